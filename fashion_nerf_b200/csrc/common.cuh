@@ -1,0 +1,69 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/fnerf.h"
+#include "layout.h"
+
+namespace fnerf {
+
+// thread-local error text behind fnerf_last_error()
+char* error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error((int)e, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+#define FN_REQUIRE(cond, code, ...) \
+  do { if (!(cond)) return ::fnerf::set_error((code), __VA_ARGS__); } while (0)
+#define FN_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)
+
+inline int num_sms() {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
+}
+
+// kernel launchers implemented in the individual .cu files (host side, return 0 / cudaError_t)
+int launch_ray_setup(const float* rays_d, float* viewdirs, float* dnorm, int64_t R, cudaStream_t s);
+int launch_stratified(const float* near, const float* far, const float* t_vals, const float* u,
+                      float* z, int64_t R, int64_t N, int lindisp, cudaStream_t s);
+int launch_importance(const float* z_c, const float* w_c, const float* u, int64_t u_stride,
+                      float* z_samples, float* z_f, int32_t* bin_idx, float* z_std, int64_t R,
+                      int64_t Nc, int64_t Nf, cudaStream_t s);
+int launch_posenc(const float* x, float* out, int64_t M, int L, cudaStream_t s);
+int launch_composite_fwd(const float* raw, const float* z, const float* dnorm, const float* noise,
+                         float* rgb, float* depth, float* acc, float* disp, float* weights,
+                         int64_t R, int64_t S, int white, cudaStream_t s);
+int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* g_rgb,
+                         const float* g_depth, const float* g_acc, float* g_raw, int64_t R,
+                         int64_t S, int white, cudaStream_t s);
+int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s);
+int launch_unpack(const void* packed, float* flat, int cond, cudaStream_t s);
+int launch_cond_project(const void* packed, const float* cond, float* proj, int64_t C, cudaStream_t s);
+
+struct MlpArgs {
+  const void* packed; int cond;
+  const float* rays_o; const float* rays_d; const float* viewdirs; const float* z;
+  const float* cond_proj; const int32_t* cond_index; int64_t C;
+  float* raw; int64_t R, S;
+};
+int launch_mlp_fp32(const MlpArgs& a, cudaStream_t s);
+int launch_mlp_tc(const MlpArgs& a, cudaStream_t s);
+
+int64_t mlp_bwd_workspace_bytes(int64_t R, int64_t S);
+int launch_mlp_bwd_fp32(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws,
+                        int64_t ws_bytes, cudaStream_t s);
+
+}  // namespace fnerf

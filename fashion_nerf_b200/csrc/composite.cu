@@ -1,0 +1,238 @@
+// Alpha compositing forward (A.5, raw2outputs) and backward (A.6).
+//
+// One warp per ray.  Samples are walked 32 at a time (lane = sample), so raw[R,S,4] is read as one
+// float4 per lane (512 contiguous bytes per warp request) and z / weights as 128-byte rows.
+// Transmittance is an exclusive product scan: a 5-step shuffle scan inside the 32-sample block
+// and a scalar carry between blocks.  The kernels are HBM-bound: 24S+36 B/ray forward,
+// 36S+24 B/ray backward.
+#include "common.cuh"
+
+namespace fnerf {
+
+constexpr int kCompWarps = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ A.5
+template <bool kHasNoise>
+__global__ void __launch_bounds__(kCompWarps * 32)
+k_composite_fwd(const float4* __restrict__ raw, const float* __restrict__ z,
+                const float* __restrict__ dnorm, const float* __restrict__ noise,
+                float* __restrict__ rgb_out, float* __restrict__ depth_out,
+                float* __restrict__ acc_out, float* __restrict__ disp_out,
+                float* __restrict__ weights, int64_t R, int S, int white) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  const int64_t warp_stride = (int64_t)gridDim.x * kCompWarps;
+  const int nblk = (S + 31) >> 5;
+
+  for (int64_t r = warp_global; r < R; r += warp_stride) {
+    const float4* rawr = raw + r * S;
+    const float* zr = z + r * S;
+    const float dn = dnorm[r];
+    float carry = 1.0f;                       // transmittance entering this 32-sample block
+    float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
+
+    // software pipeline: the next block's loads are issued before this block's scan
+    int i = lane;
+    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float zv = 0.f, nz = 0.f;
+    if (i < S) { rv = ldg_stream4(rawr + i); zv = ldg_stream(zr + i); if (kHasNoise) nz = ldg_stream(noise + r * S + i); }
+    for (int b = 0; b < nblk; ++b) {
+      const int inext = i + 32;
+      float4 rv_n = make_float4(0.f, 0.f, 0.f, 0.f);
+      float zv_n = 0.f, nz_n = 0.f;
+      if (inext < S) { rv_n = ldg_stream4(rawr + inext); zv_n = ldg_stream(zr + inext); if (kHasNoise) nz_n = ldg_stream(noise + r * S + inext); }
+
+      // z of the following sample: next lane, or lane 0 of the next block
+      float z_up = __shfl_down_sync(0xffffffffu, zv, 1);
+      const float z_first_next = __shfl_sync(0xffffffffu, zv_n, 0);
+      if (lane == 31) z_up = z_first_next;
+      const bool valid = i < S;
+      float dist = (i == S - 1) ? 1e10f : (z_up - zv);
+      dist *= dn;
+      float sigma = rv.w;
+      if (kHasNoise) sigma += nz;
+      const float alpha = valid ? (1.0f - expf(-fmaxf(sigma, 0.0f) * dist)) : 0.0f;
+      const float om = valid ? (1.0f - alpha + 1e-10f) : 1.0f;
+
+      float p = om;                           // inclusive product scan
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, p, o);
+        if (lane >= o) p *= n;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, p, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = carry * excl;
+      const float w = alpha * T;
+      carry *= __shfl_sync(0xffffffffu, p, 31);
+
+      if (valid) {
+        a_r += w * sigmoidf_(rv.x);
+        a_g += w * sigmoidf_(rv.y);
+        a_b += w * sigmoidf_(rv.z);
+        a_d += w * zv;
+        a_w += w;
+        if (weights != nullptr) weights[r * S + i] = w;
+      }
+      rv = rv_n; zv = zv_n; nz = nz_n; i = inext;
+    }
+    a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);
+    a_d = warp_sum(a_d); a_w = warp_sum(a_w);
+    if (lane == 0) {
+      const float bg = white ? (1.0f - a_w) : 0.0f;
+      rgb_out[3 * r] = a_r + bg;
+      rgb_out[3 * r + 1] = a_g + bg;
+      rgb_out[3 * r + 2] = a_b + bg;
+      depth_out[r] = a_d;
+      acc_out[r] = a_w;
+      const float q = a_d / a_w;              // NaN when acc == 0: propagated like torch.max does
+      disp_out[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
+    }
+  }
+}
+
+int launch_composite_fwd(const float* raw, const float* z, const float* dnorm, const float* noise,
+                         float* rgb, float* depth, float* acc, float* disp, float* weights,
+                         int64_t R, int64_t S, int white, cudaStream_t s) {
+  if (R == 0) return 0;
+  int64_t blocks = (R + kCompWarps - 1) / kCompWarps;
+  const int64_t cap = (int64_t)num_sms() * 8 * 4;   // 8 resident CTAs/SM x 4 waves, grid-stride beyond
+  if (blocks > cap) blocks = cap;
+  if (noise != nullptr)
+    k_composite_fwd<true><<<(unsigned)blocks, kCompWarps * 32, 0, s>>>(
+        (const float4*)raw, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white);
+  else
+    k_composite_fwd<false><<<(unsigned)blocks, kCompWarps * 32, 0, s>>>(
+        (const float4*)raw, z, dnorm, nullptr, rgb, depth, acc, disp, weights, R, (int)S, white);
+  return check_launch("composite_fwd");
+}
+
+// ------------------------------------------------------------------------------------------ A.6
+// Pass 1 (forward over the ray) computes T_i and w_i*v_i and parks them in shared memory;
+// pass 2 (backward over the ray) runs the exclusive suffix sum S_i = sum_{k>i} w_k v_k as a true
+// reverse scan and writes g_raw.  raw/z are re-read in pass 2 (L1/L2 hits; DRAM traffic is one
+// read of raw,z and one write of g_raw).
+constexpr int kBwdWarps = 4;
+
+__global__ void __launch_bounds__(kBwdWarps * 32)
+k_composite_bwd(const float4* __restrict__ raw, const float* __restrict__ z,
+                const float* __restrict__ dnorm, const float* __restrict__ g_rgb,
+                const float* __restrict__ g_depth, const float* __restrict__ g_acc,
+                float4* __restrict__ g_raw, int64_t R, int S, int white) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* s_T = smem + (size_t)warp * 2 * S;
+  float* s_wv = s_T + S;
+  const int nblk = (S + 31) >> 5;
+
+  for (int64_t r = (int64_t)blockIdx.x * kBwdWarps + warp; r < R; r += (int64_t)gridDim.x * kBwdWarps) {
+    const float4* rawr = raw + r * S;
+    const float* zr = z + r * S;
+    const float dn = dnorm[r];
+    const float gr = g_rgb[3 * r], gg = g_rgb[3 * r + 1], gb = g_rgb[3 * r + 2];
+    const float gd = g_depth ? g_depth[r] : 0.0f;
+    float ga = g_acc ? g_acc[r] : 0.0f;
+    if (white) ga -= (gr + gg + gb);
+
+    float carry = 1.0f;
+    for (int b = 0; b < nblk; ++b) {
+      const int i = b * 32 + lane;
+      const bool valid = i < S;
+      float4 rv = valid ? rawr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float zv = valid ? zr[i] : 0.f;
+      const float z_up = (i + 1 < S) ? zr[i + 1] : 0.f;
+      float dist = (i == S - 1) ? 1e10f : (z_up - zv);
+      dist *= dn;
+      const float alpha = valid ? (1.0f - expf(-fmaxf(rv.w, 0.0f) * dist)) : 0.0f;
+      const float om = valid ? (1.0f - alpha + 1e-10f) : 1.0f;
+      float p = om;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, p, o);
+        if (lane >= o) p *= n;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, p, 1);
+      if (lane == 0) excl = 1.0f;
+      const float T = carry * excl;
+      carry *= __shfl_sync(0xffffffffu, p, 31);
+      if (valid) {
+        const float v = gr * sigmoidf_(rv.x) + gg * sigmoidf_(rv.y) + gb * sigmoidf_(rv.z) + gd * zv + ga;
+        s_T[i] = T;
+        s_wv[i] = alpha * T * v;
+      }
+    }
+    __syncwarp();
+
+    float tail = 0.0f;                        // sum of w*v over all later blocks
+    for (int b = nblk - 1; b >= 0; --b) {
+      const int i = b * 32 + lane;
+      const bool valid = i < S;
+      const float wv = valid ? s_wv[i] : 0.0f;
+      float q = wv;                           // inclusive suffix scan inside the block
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_down_sync(0xffffffffu, q, o);
+        if (lane + o < 32) q += n;
+      }
+      const float suffix = (q - wv) + tail;   // exclusive
+      tail += __shfl_sync(0xffffffffu, q, 0);
+      if (valid) {
+        const float4 rv = rawr[i];
+        const float zv = zr[i];
+        const float z_up = (i + 1 < S) ? zr[i + 1] : 0.f;
+        float dist = (i == S - 1) ? 1e10f : (z_up - zv);
+        dist *= dn;
+        const float alpha = 1.0f - expf(-fmaxf(rv.w, 0.0f) * dist);
+        const float om = 1.0f - alpha + 1e-10f;
+        const float T = s_T[i];
+        const float w = alpha * T;
+        const float cr = sigmoidf_(rv.x), cg = sigmoidf_(rv.y), cb = sigmoidf_(rv.z);
+        const float v = gr * cr + gg * cg + gb * cb + gd * zv + ga;
+        const float g_alpha = T * v - suffix / om;
+        const float g_sigma = (rv.w > 0.0f) ? dist * (1.0f - alpha) * g_alpha : 0.0f;
+        g_raw[r * S + i] = make_float4(w * gr * cr * (1.0f - cr), w * gg * cg * (1.0f - cg),
+                                       w * gb * cb * (1.0f - cb), g_sigma);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* g_rgb,
+                         const float* g_depth, const float* g_acc, float* g_raw, int64_t R,
+                         int64_t S, int white, cudaStream_t s) {
+  if (R == 0) return 0;
+  const size_t smem = (size_t)kBwdWarps * 2 * S * sizeof(float);
+  if (smem > 200 * 1024) return set_error(FNERF_ERR_SIZE, "composite_bwd: S too large");
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error((int)e, "composite_bwd: %s", cudaGetErrorString(e));
+  }
+  int64_t blocks = (R + kBwdWarps - 1) / kBwdWarps;
+  const int64_t cap = (int64_t)num_sms() * 64;
+  if (blocks > cap) blocks = cap;
+  k_composite_bwd<<<(unsigned)blocks, kBwdWarps * 32, smem, s>>>(
+      (const float4*)raw, z, dnorm, g_rgb, g_depth, g_acc, (float4*)g_raw, R, (int)S, white);
+  return check_launch("composite_bwd");
+}
+
+}  // namespace fnerf

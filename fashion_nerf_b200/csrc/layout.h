@@ -1,0 +1,98 @@
+// Shared layout constants: the "flat" fp32 parameter buffer (include/fnerf.h) and the "packed"
+// device blob the kernels read.  Network shape: SURVEY.md A.4 (8x256, skip after layer 4,
+// view branch 283->128->3) and A.8 (layer 5 widened by a 256-d garment code).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FN_HD __host__ __device__ __forceinline__
+#else
+#define FN_HD inline
+#endif
+
+namespace fnerf {
+
+constexpr int kW = 256;          // trunk width
+constexpr int kPE = 63;          // 3 + 6*10
+constexpr int kPED = 27;         // 3 + 6*4
+constexpr int kLX = 10, kLD = 4; // octaves
+constexpr int kCond = 256;       // garment code width
+constexpr int kWV = 128;         // view-branch width
+constexpr int kNumLayers = 12;   // pts 0..7, alpha, feature, views, rgb
+
+// ---- flat fp32 layout ------------------------------------------------------------------------
+struct LayerDim { int out, in; };
+FN_HD LayerDim layer_dim(int l, int cond) {
+  if (l == 0) return {kW, kPE};
+  if (l == 5) return {kW, kPE + (cond ? kCond : 0) + kW};
+  if (l < 8) return {kW, kW};
+  if (l == 8) return {1, kW};          // alpha_linear
+  if (l == 9) return {kW, kW};         // feature_linear
+  if (l == 10) return {kWV, kW + kPED}; // views_linears.0
+  return {3, kWV};                     // rgb_linear
+}
+FN_HD int64_t flat_weight_offset(int l, int cond) {
+  int64_t off = 0;
+  for (int i = 0; i < l; ++i) { LayerDim d = layer_dim(i, cond); off += (int64_t)d.out * d.in + d.out; }
+  return off;
+}
+FN_HD int64_t flat_bias_offset(int l, int cond) {
+  LayerDim d = layer_dim(l, cond);
+  return flat_weight_offset(l, cond) + (int64_t)d.out * d.in;
+}
+FN_HD int64_t flat_count(int cond) { return flat_weight_offset(kNumLayers, cond); }
+
+// ---- packed blob -----------------------------------------------------------------------------
+// Section A: bf16 UMMA chunk stream, consumption order.  A chunk is ROWS x 64 bf16, K-major,
+// 128-byte swizzle (byte (r, c16) at r*128 + ((c16 ^ (r & 7)) << 4)), i.e. the exact shared-memory
+// image one bulk-TMA copy drops into a pipeline stage.
+//   chunk 0        : L0   [256 x 64]  cols 0..62 = W0, col 63 = 0
+//   chunks 1..16   : L1..L4, 4 K-chunks each
+//   chunk 17       : L5 positional block W5[:,0:63] (+ zero col)
+//   chunks 18..21  : L5 trunk block W5[:, hoff + 64*kb ..], hoff = 63 (+256 when cond)
+//   chunks 22..29  : L6, L7
+//   chunks 30..33  : feature_linear
+//   chunks 34..37  : views_linears.0 trunk block [128 x 64] each (16 KB)
+//   chunk 38       : views_linears.0 direction block [128 x 64], cols 0..26 = Wv[:,256:283]
+constexpr int kChunkK = 64;
+constexpr int kBigChunks = 34;
+constexpr int kSmallChunks = 5;
+constexpr int kNumChunks = kBigChunks + kSmallChunks;
+constexpr int kBigChunkBytes = 256 * kChunkK * 2;   // 32768
+constexpr int kSmallChunkBytes = 128 * kChunkK * 2; // 16384
+constexpr int64_t kSecABytes = (int64_t)kBigChunks * kBigChunkBytes + (int64_t)kSmallChunks * kSmallChunkBytes;
+FN_HD int64_t chunk_offset(int c) {
+  return c < kBigChunks ? (int64_t)c * kBigChunkBytes
+                        : (int64_t)kBigChunks * kBigChunkBytes + (int64_t)(c - kBigChunks) * kSmallChunkBytes;
+}
+FN_HD int chunk_bytes(int c) { return c < kBigChunks ? kBigChunkBytes : kSmallChunkBytes; }
+
+// Section B: fp32 "aux" (biases and the two tiny heads), offsets in floats.
+constexpr int kAuxBiasPts = 0;        // 8 x 256
+constexpr int kAuxBiasFeat = 2048;    // 256
+constexpr int kAuxBiasViews = 2304;   // 128
+constexpr int kAuxWAlpha = 2432;      // 256
+constexpr int kAuxBAlpha = 2688;      // 1 (+3 pad)
+constexpr int kAuxWRgb = 2692;        // 3 x 128
+constexpr int kAuxBRgb = 3076;        // 3 (+pad)
+constexpr int kAuxFloats = 3088;
+constexpr int64_t kSecBOffset = kSecABytes;
+constexpr int64_t kSecBBytes = (int64_t)kAuxFloats * 4;
+
+// Section C: fp32 K-major (transposed) weights for the SIMT path: layer l stored as [in][out].
+// Order: pts 0..7, feature, views.  (alpha / rgb live in aux.)
+constexpr int64_t kSecCOffset = kSecBOffset + kSecBBytes;
+FN_HD int simt_layer_id(int j) { return j < 8 ? j : (j == 8 ? 9 : 10); }  // j-th SIMT layer -> flat layer
+FN_HD int64_t simt_offset_floats(int j, int cond) {
+  int64_t off = 0;
+  for (int i = 0; i < j; ++i) { LayerDim d = layer_dim(simt_layer_id(i), cond); off += (int64_t)d.out * d.in; }
+  return off;
+}
+FN_HD int64_t packed_bytes(int cond) { return kSecCOffset + simt_offset_floats(10, cond) * 4; }
+
+// swizzled byte offset of element (row r, column k in [0,64)) inside a chunk / activation K-block
+FN_HD uint32_t sw128_offset(uint32_t r, uint32_t k) {
+  return r * 128u + ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));
+}
+
+}  // namespace fnerf

@@ -1,0 +1,160 @@
+// Weight packer / unpacker (flat fp32 nn.Linear layout <-> packed device blob, see layout.h),
+// standalone positional encoding (A.3) and the hoisted conditioning projection (A.8).
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace fnerf {
+
+struct ChunkSrc { int layer, rows, colbase, valid; };
+__host__ __device__ inline ChunkSrc chunk_src(int c, int cond) {
+  const int hoff = kPE + (cond ? kCond : 0);
+  if (c == 0) return {0, 256, 0, kPE};
+  if (c <= 16) return {1 + (c - 1) / 4, 256, ((c - 1) % 4) * 64, 64};
+  if (c == 17) return {5, 256, 0, kPE};
+  if (c <= 21) return {5, 256, hoff + (c - 18) * 64, 64};
+  if (c <= 29) return {6 + (c - 22) / 4, 256, ((c - 22) % 4) * 64, 64};
+  if (c <= 33) return {9, 256, (c - 30) * 64, 64};
+  if (c <= 37) return {10, 128, (c - 34) * 64, 64};
+  return {10, 128, 256, kPED};
+}
+
+__global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict__ packed, int cond) {
+  const int64_t total = (int64_t)kBigChunks * 256 * 64 + (int64_t)kSmallChunks * 128 * 64;
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  int c, within;
+  const int64_t big = (int64_t)kBigChunks * 256 * 64;
+  if (e < big) { c = (int)(e / (256 * 64)); within = (int)(e % (256 * 64)); }
+  else { c = kBigChunks + (int)((e - big) / (128 * 64)); within = (int)((e - big) % (128 * 64)); }
+  const int r = within >> 6, k = within & 63;
+  const ChunkSrc cs = chunk_src(c, cond);
+  const LayerDim d = layer_dim(cs.layer, cond);
+  float v = 0.0f;
+  if (k < cs.valid) v = flat[flat_weight_offset(cs.layer, cond) + (int64_t)r * d.in + cs.colbase + k];
+  __nv_bfloat16 b = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(packed + chunk_offset(c) + sw128_offset(r, k)) = b;
+}
+
+__global__ void k_pack_aux(const float* __restrict__ flat, float* __restrict__ aux, int cond) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kAuxFloats) return;
+  float v = 0.0f;
+  if (i < kAuxBiasFeat) v = flat[flat_bias_offset(i >> 8, cond) + (i & 255)];
+  else if (i < kAuxBiasViews) v = flat[flat_bias_offset(9, cond) + (i - kAuxBiasFeat)];
+  else if (i < kAuxWAlpha) v = flat[flat_bias_offset(10, cond) + (i - kAuxBiasViews)];
+  else if (i < kAuxBAlpha) v = flat[flat_weight_offset(8, cond) + (i - kAuxWAlpha)];
+  else if (i == kAuxBAlpha) v = flat[flat_bias_offset(8, cond)];
+  else if (i >= kAuxWRgb && i < kAuxBRgb) v = flat[flat_weight_offset(11, cond) + (i - kAuxWRgb)];
+  else if (i >= kAuxBRgb && i < kAuxBRgb + 3) v = flat[flat_bias_offset(11, cond) + (i - kAuxBRgb)];
+  aux[i] = v;
+}
+
+// Section C: layer j stored K-major: wt[k][n] = W[n][k]
+__global__ void k_pack_simt(const float* __restrict__ flat, float* __restrict__ secC, int cond, int j) {
+  const int l = simt_layer_id(j);
+  const LayerDim d = layer_dim(l, cond);
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)d.out * d.in) return;
+  const int k = (int)(e / d.out), n = (int)(e % d.out);
+  secC[simt_offset_floats(j, cond) + e] = flat[flat_weight_offset(l, cond) + (int64_t)n * d.in + k];
+}
+
+__global__ void k_unpack(const uint8_t* __restrict__ packed, float* __restrict__ flat, int cond) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= flat_count(cond)) return;
+  // locate layer
+  int l = 0;
+  while (l + 1 < kNumLayers && e >= flat_weight_offset(l + 1, cond)) ++l;
+  const LayerDim d = layer_dim(l, cond);
+  const int64_t within = e - flat_weight_offset(l, cond);
+  const float* aux = reinterpret_cast<const float*>(packed + kSecBOffset);
+  const float* secC = reinterpret_cast<const float*>(packed + kSecCOffset);
+  float v;
+  if (within >= (int64_t)d.out * d.in) {            // bias
+    const int n = (int)(within - (int64_t)d.out * d.in);
+    if (l < 8) v = aux[kAuxBiasPts + l * 256 + n];
+    else if (l == 8) v = aux[kAuxBAlpha];
+    else if (l == 9) v = aux[kAuxBiasFeat + n];
+    else if (l == 10) v = aux[kAuxBiasViews + n];
+    else v = aux[kAuxBRgb + n];
+  } else {
+    const int n = (int)(within / d.in), k = (int)(within % d.in);
+    if (l == 8) v = aux[kAuxWAlpha + k];
+    else if (l == 11) v = aux[kAuxWRgb + n * kWV + k];
+    else {
+      const int j = l < 8 ? l : (l == 9 ? 8 : 9);
+      v = secC[simt_offset_floats(j, cond) + (int64_t)k * d.out + n];
+    }
+  }
+  flat[e] = v;
+}
+
+int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(packed);
+  const int64_t total = (int64_t)kBigChunks * 256 * 64 + (int64_t)kSmallChunks * 128 * 64;
+  k_pack_bf16<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(flat, p, cond);
+  k_pack_aux<<<(kAuxFloats + 255) / 256, 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecBOffset), cond);
+  for (int j = 0; j < 10; ++j) {
+    const LayerDim d = layer_dim(simt_layer_id(j), cond);
+    const int64_t n = (int64_t)d.out * d.in;
+    k_pack_simt<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecCOffset), cond, j);
+  }
+  return check_launch("pack_weights");
+}
+
+int launch_unpack(const void* packed, float* flat, int cond, cudaStream_t s) {
+  const int64_t n = flat_count(cond);
+  k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(packed), flat, cond);
+  return check_launch("unpack_weights");
+}
+
+// ------------------------------------------------------------------------------------------ A.3
+__global__ void k_posenc(const float* __restrict__ x, float* __restrict__ out, int64_t M, int L) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int width = 3 + 6 * L;
+  if (idx >= M * 3) return;
+  const int64_t m = idx / 3;
+  const int c = (int)(idx % 3);
+  const float v = x[idx];
+  float* o = out + m * width;
+  o[c] = v;
+  float f = 1.0f;
+  for (int k = 0; k < L; ++k) {
+    float s, co;
+    sincosf(__fmul_rn(v, f), &s, &co);
+    o[3 + 6 * k + c] = s;
+    o[3 + 6 * k + 3 + c] = co;
+    f *= 2.0f;
+  }
+}
+
+int launch_posenc(const float* x, float* out, int64_t M, int L, cudaStream_t s) {
+  if (M == 0) return 0;
+  k_posenc<<<(unsigned)((M * 3 + 255) / 256), 256, 0, s>>>(x, out, M, L);
+  return check_launch("posenc");
+}
+
+// ------------------------------------------------------------------------------------------ A.8
+// proj[c][n] = sum_k cond[c][k] * W5[n][63 + k]  (fp32; W5 read from the K-major SIMT section)
+__global__ void k_cond_project(const uint8_t* __restrict__ packed, const float* __restrict__ cond,
+                               float* __restrict__ proj, int64_t C) {
+  __shared__ float s_c[kCond];
+  const float* w5t = reinterpret_cast<const float*>(packed + kSecCOffset) + simt_offset_floats(5, 1);
+  for (int64_t c = blockIdx.x; c < C; c += gridDim.x) {
+    __syncthreads();
+    s_c[threadIdx.x] = cond[c * kCond + threadIdx.x];
+    __syncthreads();
+    float acc = 0.0f;
+    for (int k = 0; k < kCond; ++k) acc = fmaf(s_c[k], w5t[(int64_t)(kPE + k) * kW + threadIdx.x], acc);
+    proj[c * kW + threadIdx.x] = acc;
+  }
+}
+
+int launch_cond_project(const void* packed, const float* cond, float* proj, int64_t C, cudaStream_t s) {
+  if (C == 0) return 0;
+  int64_t blocks = C < 65535 ? C : 65535;
+  k_cond_project<<<(unsigned)blocks, kW, 0, s>>>(reinterpret_cast<const uint8_t*>(packed), cond, proj, C);
+  return check_launch("cond_project");
+}
+
+}  // namespace fnerf

@@ -1,0 +1,216 @@
+"""render_rays: the Python operator boundary.
+
+``render_rays(model, rays_o, rays_d, near, far, N_samples, N_importance, cond=None, ...)`` is the
+public call; it lowers to the torch custom op ``fnerf::render_rays`` (fake-tensor and autograd
+registered), which makes ONE C-ABI call, ``fnerf_render_rays``, that enqueues the whole
+coarse -> composite -> importance -> fine -> composite chain on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, ops
+from .model import NerfModel
+
+_T = torch.Tensor
+_tvals_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def _linspace01(n: int, device) -> torch.Tensor:
+    """torch.linspace evaluated on the CPU (the oracle's bits: linspace(0,1,n)[i] != i/(n-1)) and
+    cached on the device."""
+    key = (n, str(device))
+    t = _tvals_cache.get(key)
+    if t is None:
+        t = torch.linspace(0.0, 1.0, n).to(device)
+        _tvals_cache[key] = t
+    return t
+
+
+def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c, cond_proj_f,
+                 cond_index, n_importance, white_bkgd, lindisp, precision) -> List[_T]:
+    lib = _lib.load()
+    dev = rays_o.device
+    R, Nc, Nf = rays_o.shape[0], t_vals.numel(), int(n_importance)
+    S = Nc + Nf
+
+    def new(*shape):
+        return torch.empty(*shape, dtype=torch.float32, device=dev)
+
+    rgb, disp, acc, depth = new(R, 3), new(R), new(R), new(R)
+    rgb0, disp0, acc0, z_std = new(R, 3), new(R), new(R), new(R)
+    z_c, raw_c, w_c = new(R, Nc), new(R, Nc, 4), new(R, Nc)
+    z_f, raw_f = (new(R, S), new(R, S, 4)) if Nf > 0 else (new(0), new(0))
+    ws_bytes = int(lib.fnerf_render_rays_workspace_bytes(R, Nc, Nf))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+
+    a = _lib.RenderArgs()
+    p = ops._ptr
+    a.packed_coarse, a.packed_fine = packed_c.data_ptr(), packed_f.data_ptr()
+    a.cond = int(cond_proj_c is not None)
+    a.precision = int(precision)
+    a.rays_o, a.rays_d, a.near, a.far = rays_o.data_ptr(), rays_d.data_ptr(), near.data_ptr(), far.data_ptr()
+    a.t_vals, a.u_strat = t_vals.data_ptr(), p(u_strat)
+    a.u_fine = p(u_fine)
+    a.u_fine_row_stride = 0 if (u_fine is None or u_fine.dim() == 1) else Nf
+    a.cond_proj_coarse, a.cond_proj_fine, a.cond_index = p(cond_proj_c), p(cond_proj_f), p(cond_index)
+    a.C = 0 if cond_proj_c is None else cond_proj_c.shape[0]
+    a.R, a.Nc, a.Nf = R, Nc, Nf
+    a.white_bkgd, a.lindisp = int(white_bkgd), int(lindisp)
+    a.rgb, a.disp, a.acc, a.depth = rgb.data_ptr(), disp.data_ptr(), acc.data_ptr(), depth.data_ptr()
+    a.rgb0, a.disp0, a.acc0, a.z_std = rgb0.data_ptr(), disp0.data_ptr(), acc0.data_ptr(), z_std.data_ptr()
+    a.z_c, a.raw_c, a.weights_c = z_c.data_ptr(), raw_c.data_ptr(), w_c.data_ptr()
+    if Nf > 0:
+        a.z_f, a.raw_f = z_f.data_ptr(), raw_f.data_ptr()
+    a.weights_f = None
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    with torch.cuda.device(dev):
+        _lib.check(lib.fnerf_render_rays(ctypes.byref(a), torch.cuda.current_stream().cuda_stream), "render_rays")
+    return [rgb, disp, acc, depth, rgb0, disp0, acc0, z_std, z_c, z_f, raw_c, raw_f]
+
+
+@torch.library.custom_op("fnerf::render_rays", mutates_args=())
+def render_rays_op(flat_c: _T, flat_f: _T, packed_c: _T, packed_f: _T, rays_o: _T, rays_d: _T, near: _T, far: _T,
+                   t_vals: _T, u_strat: Optional[_T], u_fine: Optional[_T], cond_proj_c: Optional[_T],
+                   cond_proj_f: Optional[_T], cond_index: Optional[_T], n_importance: int, white_bkgd: bool,
+                   lindisp: bool, precision: int) -> List[_T]:
+    # flat_c / flat_f only anchor the autograd graph; the kernels read the packed blobs.
+    return _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c,
+                        cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision)
+
+
+@render_rays_op.register_fake
+def _(flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c,
+      cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision):
+    R, Nc, S = rays_o.shape[0], t_vals.numel(), t_vals.numel() + n_importance
+    e = rays_o.new_empty
+    zf, rf = (e(R, S), e(R, S, 4)) if n_importance > 0 else (e(0), e(0))
+    return [e(R, 3), e(R), e(R), e(R), e(R, 3), e(R), e(R), e(R), e(R, Nc), zf, e(R, Nc, 4), rf]
+
+
+def _setup_context(ctx, inputs, output):
+    (flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c,
+     cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision) = inputs
+    z_c, z_f, raw_c, raw_f = output[8], output[9], output[10], output[11]
+    ctx.save_for_backward(packed_c, packed_f, rays_o, rays_d, z_c, z_f, raw_c, raw_f, cond_proj_c, cond_proj_f,
+                          cond_index)
+    ctx.n_importance, ctx.white_bkgd, ctx.precision = n_importance, white_bkgd, precision
+    ctx.n_c, ctx.n_f = flat_c.numel(), flat_f.numel()
+
+
+def _backward(ctx, grads):
+    """A.6 + MLP backward for the training loss (grads w.r.t. rgb/acc/depth maps; disp and z_std carry
+    none in A.10).  Sample positions are detached (A.7)."""
+    packed_c, packed_f, rays_o, rays_d, z_c, z_f, raw_c, raw_f, cpc, cpf, cidx = ctx.saved_tensors
+    g_rgb, _g_disp, g_acc, g_depth, g_rgb0, _g_disp0, g_acc0 = grads[:7]
+    viewdirs, dnorm = ops.ray_setup(rays_d)
+    R = rays_o.shape[0]
+    dev = rays_o.device
+    zeros3 = None
+
+    def grad_net(packed, z, raw, gr, gd, ga, n_params, cp):
+        nonlocal zeros3
+        if gr is None and gd is None and ga is None:
+            return None
+        if gr is None:
+            zeros3 = torch.zeros(R, 3, device=dev) if zeros3 is None else zeros3
+            gr = zeros3
+        g_raw = ops.composite_bwd(raw, z, dnorm, gr.contiguous(), gd, ga, white_bkgd=ctx.white_bkgd)
+        flat_grad = torch.zeros(n_params, dtype=torch.float32, device=dev)
+        ops.mlp_bwd(packed, rays_o, rays_d, viewdirs, z, g_raw, flat_grad, cond_proj=cp, cond_index=cidx)
+        return flat_grad
+
+    if ctx.n_importance > 0:
+        g_flat_f = grad_net(packed_f, z_f, raw_f, g_rgb, g_depth, g_acc, ctx.n_f, cpf)
+        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb0, None, g_acc0, ctx.n_c, cpc)
+    else:
+        g_flat_f = None
+        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb, g_depth, g_acc, ctx.n_c, cpc)
+    return (g_flat_c, g_flat_f) + (None,) * 16
+
+
+render_rays_op.register_autograd(_backward, setup_context=_setup_context)
+
+_OUT_NAMES = ["rgb", "disp", "acc", "depth", "rgb0", "disp0", "acc0", "z_std", "z_c", "z_f", "raw_c", "raw_f"]
+
+
+def _per_ray(v, R: int, device, name: str) -> torch.Tensor:
+    if torch.is_tensor(v):
+        t = v.to(device=device, dtype=torch.float32).reshape(-1)
+        if t.numel() == 1:
+            t = t.expand(R)
+        if t.numel() != R:
+            raise ValueError(f"{name} must be a float or have R={R} elements")
+        return t.contiguous()
+    return torch.full((R,), float(v), dtype=torch.float32, device=device)
+
+
+def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, near, far, N_samples: int,
+                N_importance: int, cond: Optional[torch.Tensor] = None, *, view_id: Optional[torch.Tensor] = None,
+                u_strat: Optional[torch.Tensor] = None, u_fine: Optional[torch.Tensor] = None,
+                white_bkgd: bool = False, lindisp: bool = False, precision: str = "bf16",
+                return_taps: bool = False) -> Dict[str, torch.Tensor]:
+    """Volume-render a batch of rays (A.9).
+
+    rays_o, rays_d: [R,3] CUDA fp32 (rays_d un-normalised).  near/far: floats or [R]/[R,1] tensors.
+    cond: None | [256] | [R,256] | [V,256] with view_id[R] (A.8; requires a model built with cond=True).
+    u_strat [R,N_samples] / u_fine [R,N_importance]: caller-supplied uniforms; None = deterministic
+    (no jitter; u_fine = linspace(0,1,N_importance)).
+    Returns rgb[R,3], disp, acc, depth, rgb0, disp0, acc0, z_std (+ taps z_c, z_f, raw_c, raw_f).
+    """
+    if not rays_o.is_cuda:
+        raise _lib.FnerfError("render_rays needs CUDA tensors (no CPU fallback)")
+    dev = rays_o.device
+    R = rays_o.shape[0]
+    rays_o = rays_o.float().contiguous()
+    rays_d = rays_d.float().contiguous()
+    near_t, far_t = _per_ray(near, R, dev, "near"), _per_ray(far, R, dev, "far")
+    t_vals = _linspace01(N_samples, dev)
+    if u_strat is not None:
+        u_strat = u_strat.float().contiguous()
+        assert u_strat.shape == (R, N_samples)
+    if N_importance > 0:
+        if u_fine is None:
+            u_fine = _linspace01(N_importance, dev)
+        else:
+            u_fine = u_fine.float().contiguous()
+            assert u_fine.shape == (R, N_importance)
+    cpc = cpf = cidx = None
+    if cond is not None:
+        if not model.cond:
+            raise ValueError("cond given but the model was built without the conditioned layer 5")
+        cond = cond.to(dev).float().reshape(-1, 256)
+        if view_id is not None:
+            cidx = view_id.to(dev).to(torch.int32).contiguous()
+        elif cond.shape[0] not in (1, R):
+            raise ValueError("cond must be [256], [R,256], or [V,256] with view_id")
+        cpc = ops.cond_project(model.coarse.packed, cond)
+        cpf = ops.cond_project(model.fine.packed, cond)
+    elif model.cond:
+        raise ValueError("model expects cond")
+    outs = render_rays_op(model.coarse.flat, model.fine.flat, model.coarse.packed, model.fine.packed, rays_o, rays_d,
+                          near_t, far_t, t_vals, u_strat, u_fine if N_importance > 0 else None, cpc, cpf, cidx,
+                          int(N_importance), bool(white_bkgd), bool(lindisp), ops.PRECISIONS[precision])
+    n = len(_OUT_NAMES) if return_taps else 8
+    return {k: v for k, v in zip(_OUT_NAMES[:n], outs[:n])}
+
+
+def render_image(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, near, far, N_samples: int,
+                 N_importance: int, cond=None, *, chunk: int = 1 << 16, **kw) -> Dict[str, torch.Tensor]:
+    """Full-frame render: chunk the flattened ray list through render_rays."""
+    keys = ("rgb", "disp", "acc", "depth", "rgb0", "disp0", "acc0", "z_std")
+    parts = {k: [] for k in keys}
+    R = rays_o.shape[0]
+    per_ray = {k: kw.pop(k) for k in ("u_strat", "u_fine", "view_id") if k in kw}
+    with torch.no_grad():
+        for s in range(0, R, chunk):
+            sl = slice(s, min(s + chunk, R))
+            extra = {k: (v[sl] if v is not None else None) for k, v in per_ray.items()}
+            c = cond[sl] if (cond is not None and cond.dim() == 2 and cond.shape[0] == R) else cond
+            out = render_rays(model, rays_o[sl], rays_d[sl], near, far, N_samples, N_importance, c, **extra, **kw)
+            for k in keys:
+                parts[k].append(out[k])
+    return {k: torch.cat(v, 0) for k, v in parts.items()}
