@@ -1,5 +1,352 @@
-// placeholder until the tcgen05 kernel lands
+// Fused bf16 tensor-core network query (A.3 + A.4 + A.8) for sm_100a: tcgen05.mma with TMEM
+// accumulators, weights streamed by bulk TMA, activations resident in shared memory.
+//
+// One persistent CTA per SM walks 128-sample tiles.  Warp roles (192 threads):
+//   warp 0      weight producer: one lane streams the 39 pre-swizzled weight chunks of the network
+//               (layout.h section A, consumption order) through a ring of 32 KB stages with
+//               cp.async.bulk + mbarrier complete_tx;
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=256|128, K=16) for every layer,
+//               A = activation / encoding tile in smem (K-major, 128B swizzle), B = weight stage,
+//               D = one of two 128x256 fp32 accumulators in TMEM (layer parity);
+//   warps 2..5  workers: build the positional-encoding tiles for their row (sample), and run the
+//               per-layer epilogue: tcgen05.ld 64 columns -> +bias (+hoisted cond projection)
+//               -> ReLU -> bf16 -> swizzled st.shared as the next layer's A operand.
+// The epilogue hands the activation tile over in 64-column K-blocks (one mbarrier each), so the
+// next layer's MMAs on K-block 0 start while the epilogue is still converting K-blocks 1..3; the
+// two TMEM accumulators make that overlap legal.  Encoded samples and activations never touch HBM:
+// per sample the kernel reads 4 B (z) and writes 16 B (raw).
+// sigma (256->1) and rgb (128->3) are fp32 dot products inside the epilogues of layer 7 and of the
+// view layer.
 #include "common.cuh"
+#include "tc_ptx.cuh"
+
 namespace fnerf {
-int launch_mlp_tc(const MlpArgs&, cudaStream_t) { return set_error(FNERF_ERR_ARG, "mlp_tc: not built"); }
+using namespace ptx;
+
+constexpr int kTileM = 128;
+constexpr int kStages = 3;
+constexpr int kTcThreads = 192;
+constexpr uint32_t kKBlockBytes = kTileM * 128;                 // 16 KB: 128 rows x 64 bf16
+constexpr uint32_t kOffAct = 0;                                 // 4 K-blocks
+constexpr uint32_t kOffPe = 4 * kKBlockBytes;                   // xyz encoding (63 -> 64)
+constexpr uint32_t kOffPed = kOffPe + kKBlockBytes;             // direction encoding (27 -> 32 used)
+constexpr uint32_t kOffW = kOffPed + kKBlockBytes;              // weight stages
+constexpr uint32_t kOffAux = kOffW + kStages * kBigChunkBytes;  // fp32 biases + heads
+constexpr uint32_t kOffBar = kOffAux + kAuxFloats * 4;
+constexpr uint32_t kNumBars = 2 * kStages + 4 + 1 + 2;
+constexpr uint32_t kTcSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;  // + tmem ptr + alignment slack
+static_assert(kOffBar % 8 == 0, "barrier alignment");
+static_assert(kTcSmemBytes <= 227 * 1024, "shared memory budget");
+
+struct TcParams {
+  const uint8_t* packed;
+  const float* rays_o; const float* rays_d; const float* viewdirs; const float* z;
+  const float* cond_proj; const int32_t* cond_index; int64_t C;
+  float4* raw;
+  int64_t M; int S; int64_t ntiles; int cond;
+};
+
+// epilogue of one 64-column K-block: TMEM -> (+bias, +rowbias) -> [ReLU] -> bf16 -> swizzled smem
+template <bool kRelu, bool kSigma, bool kCond>
+__device__ __forceinline__ void epilogue_kblock(uint32_t taddr, const float* __restrict__ bias_s,
+                                                const float* __restrict__ walpha_s,
+                                                const float* __restrict__ rowbias, uint32_t act_row_addr,
+                                                uint32_t row, float& sigma) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32(taddr, v0);
+  tmem_ld32(taddr + 32, v1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {          // 16-byte chunk = 8 columns
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(h == 0 ? v0[c * 8 + j] : v1[c * 8 + j]);
+      const int col = h * 32 + c * 8;
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 4);
+      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+      if (kCond) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rowbias + col));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rowbias + col + 4));
+        x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+        x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+      }
+      if (kSigma) {
+        const float4 w0 = *reinterpret_cast<const float4*>(walpha_s + col);
+        const float4 w1 = *reinterpret_cast<const float4*>(walpha_s + col + 4);
+        sigma = fmaf(fmaxf(x[0], 0.f), w0.x, sigma); sigma = fmaf(fmaxf(x[1], 0.f), w0.y, sigma);
+        sigma = fmaf(fmaxf(x[2], 0.f), w0.z, sigma); sigma = fmaf(fmaxf(x[3], 0.f), w0.w, sigma);
+        sigma = fmaf(fmaxf(x[4], 0.f), w1.x, sigma); sigma = fmaf(fmaxf(x[5], 0.f), w1.y, sigma);
+        sigma = fmaf(fmaxf(x[6], 0.f), w1.z, sigma); sigma = fmaf(fmaxf(x[7], 0.f), w1.w, sigma);
+      }
+      uint32_t p0, p1, p2, p3;
+      if (kRelu) {
+        p0 = pack_bf16_relu(x[0], x[1]); p1 = pack_bf16_relu(x[2], x[3]);
+        p2 = pack_bf16_relu(x[4], x[5]); p3 = pack_bf16_relu(x[6], x[7]);
+      } else {
+        p0 = pack_bf16(x[0], x[1]); p1 = pack_bf16(x[2], x[3]);
+        p2 = pack_bf16(x[4], x[5]); p3 = pack_bf16(x[6], x[7]);
+      }
+      const uint32_t c16 = (uint32_t)(h * 4 + c);
+      st_shared_v4(act_row_addr + ((c16 ^ (row & 7u)) << 4), p0, p1, p2, p3);
+    }
+  }
 }
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kOffBar;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto bar_act = [&](int kb) { return bar0 + 8u * (2 * kStages + kb); };
+  const uint32_t bar_pe = bar0 + 8u * (2 * kStages + 4);
+  auto bar_acc = [&](int a) { return bar0 + 8u * (2 * kStages + 5 + a); };
+  const uint32_t tmem_slot = bar0 + 8u * kNumBars;
+  float* aux_s = reinterpret_cast<float*>(base_ptr + kOffAux);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  {
+    const float* aux_g = reinterpret_cast<const float*>(P.packed + kSecBOffset);
+    for (int i = threadIdx.x; i < kAuxFloats; i += kTcThreads) aux_s[i] = aux_g[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 128);
+    mbar_init(bar_pe, 128);
+    mbar_init(bar_acc(0), 1);
+    mbar_init(bar_acc(1), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBar + 8 * kNumBars);
+
+  const int64_t first_tile = blockIdx.x;
+  const int64_t tile_stride = gridDim.x;
+
+  if (warp == 0) {
+    // ================================ weight producer ==============================================
+    if (lane == 0) {
+      uint32_t wc = 0;
+      for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride) {
+        for (int c = 0; c < kNumChunks; ++c, ++wc) {
+          const uint32_t s = wc % kStages;
+          mbar_wait(bar_empty(s), ((wc / kStages) & 1u) ^ 1u);
+          const uint32_t bytes = (uint32_t)chunk_bytes(c);
+          mbar_expect_tx(bar_full(s), bytes);
+          bulk_g2s(base + kOffW + s * kBigChunkBytes, P.packed + chunk_offset(c), bytes, bar_full(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
+      uint32_t wc = 0, act_cnt = 0, tile_cnt = 0;
+      // consume one weight stage against `ksteps` K=16 slices of the A tile at a_addr
+      auto issue_chunk = [&](uint32_t a_addr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool first) {
+        const uint32_t s = wc % kStages;
+        mbar_wait(bar_full(s), (wc / kStages) & 1u);
+        tc_fence_after();
+        const uint32_t b_addr = base + kOffW + s * kBigChunkBytes;
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16(tmem_d, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc,
+                    (first && ks == 0) ? 0u : 1u);
+        umma_commit(bar_empty(s));
+        ++wc;
+      };
+      // a 256-wide layer whose A operand is the activation tile, gated per K-block by the epilogue
+      auto trunk_layer = [&](uint32_t tmem_d, uint32_t idesc, bool first_is_fresh) {
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(bar_act(kb), act_cnt & 1u);
+          tc_fence_after();
+          issue_chunk(base + kOffAct + kb * kKBlockBytes, 4, idesc, tmem_d, first_is_fresh && kb == 0);
+        }
+        ++act_cnt;
+      };
+      const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256;
+      for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride, ++tile_cnt) {
+        mbar_wait(bar_pe, tile_cnt & 1u);
+        tc_fence_after();
+        issue_chunk(base + kOffPe, 4, idesc256, acc0, true);                    // L0
+        umma_commit(bar_acc(0));
+        for (int l = 1; l <= 4; ++l) {                                          // L1..L4
+          trunk_layer((l & 1) ? acc1 : acc0, idesc256, true);
+          umma_commit(bar_acc(l & 1));
+        }
+        issue_chunk(base + kOffPe, 4, idesc256, acc1, true);                    // L5: encoding block
+        trunk_layer(acc1, idesc256, false);                                     //     + trunk block
+        umma_commit(bar_acc(1));
+        trunk_layer(acc0, idesc256, true);  umma_commit(bar_acc(0));            // L6
+        trunk_layer(acc1, idesc256, true);  umma_commit(bar_acc(1));            // L7
+        trunk_layer(acc0, idesc256, true);  umma_commit(bar_acc(0));            // feature
+        trunk_layer(acc1, idesc128, true);                                      // views: feature block
+        issue_chunk(base + kOffPed, 2, idesc128, acc1, false);                  //        + direction block
+        umma_commit(bar_acc(1));
+      }
+    }
+  } else {
+    // ================================ workers: encodings + epilogues ===============================
+    const uint32_t q = (uint32_t)warp & 3u;
+    const uint32_t row = q * 32u + (uint32_t)lane;
+    const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
+    uint32_t acc_cnt[2] = {0u, 0u};
+    const uint32_t act_row = base + kOffAct + row * 128u;
+    for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride) {
+      const int64_t g = tile * kTileM + row;
+      const int64_t gc = g < P.M ? g : P.M - 1;
+      const int64_t ray = gc / P.S;
+      // ---- positional encodings (A.3): sincos once, then double-angle recurrence per octave -----
+      {
+        const float zv = P.z[gc];
+        float f[64];
+        f[63] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float p = __fadd_rn(P.rays_o[3 * ray + c], __fmul_rn(P.rays_d[3 * ray + c], zv));
+          f[c] = p;
+          float sn, cs;
+          sincosf(p, &sn, &cs);
+#pragma unroll
+          for (int k = 0; k < kLX; ++k) {
+            f[3 + 6 * k + c] = sn;
+            f[3 + 6 * k + 3 + c] = cs;
+            const float s2 = 2.0f * sn * cs;
+            cs = 1.0f - 2.0f * sn * sn;
+            sn = s2;
+          }
+        }
+        const uint32_t pe_row = base + kOffPe + row * 128u;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16)
+          st_shared_v4(pe_row + (((uint32_t)c16 ^ (row & 7u)) << 4),
+                       pack_bf16(f[c16 * 8 + 0], f[c16 * 8 + 1]), pack_bf16(f[c16 * 8 + 2], f[c16 * 8 + 3]),
+                       pack_bf16(f[c16 * 8 + 4], f[c16 * 8 + 5]), pack_bf16(f[c16 * 8 + 6], f[c16 * 8 + 7]));
+        float d[32];
+#pragma unroll
+        for (int i = kPED; i < 32; ++i) d[i] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float p = P.viewdirs[3 * ray + c];
+          d[c] = p;
+          float sn, cs;
+          sincosf(p, &sn, &cs);
+#pragma unroll
+          for (int k = 0; k < kLD; ++k) {
+            d[3 + 6 * k + c] = sn;
+            d[3 + 6 * k + 3 + c] = cs;
+            const float s2 = 2.0f * sn * cs;
+            cs = 1.0f - 2.0f * sn * sn;
+            sn = s2;
+          }
+        }
+        const uint32_t ped_row = base + kOffPed + row * 128u;
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16)
+          st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4),
+                       pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
+                       pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_pe);
+
+      const float* rowbias = nullptr;
+      if (P.cond) {
+        const int64_t crow = P.cond_index ? (int64_t)P.cond_index[ray] : (P.C == 1 ? 0 : ray);
+        rowbias = P.cond_proj + crow * kW;
+      }
+      float sigma = aux_s[kAuxBAlpha];
+      // ---- trunk + feature epilogues ---------------------------------------------------------------
+#pragma unroll 1
+      for (int step = 0; step < 9; ++step) {
+        const int a = step & 1;
+        mbar_wait(bar_acc(a), acc_cnt[a] & 1u);
+        ++acc_cnt[a];
+        tc_fence_after();
+        const float* bias_s = aux_s + (step < 8 ? kAuxBiasPts + step * 256 : kAuxBiasFeat);
+        const uint32_t tacc = tmem_row + (uint32_t)a * 256u;
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint32_t dst = act_row + (uint32_t)kb * kKBlockBytes;
+          if (step == 8)
+            epilogue_kblock<false, false, false>(tacc + kb * 64, bias_s + kb * 64, nullptr, nullptr, dst, row, sigma);
+          else if (step == 7)
+            epilogue_kblock<true, true, false>(tacc + kb * 64, bias_s + kb * 64, aux_s + kAuxWAlpha + kb * 64, nullptr, dst, row, sigma);
+          else if (step == 5 && P.cond)
+            epilogue_kblock<true, false, true>(tacc + kb * 64, bias_s + kb * 64, nullptr, rowbias + kb * 64, dst, row, sigma);
+          else
+            epilogue_kblock<true, false, false>(tacc + kb * 64, bias_s + kb * 64, nullptr, nullptr, dst, row, sigma);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_act(kb));
+        }
+      }
+      // ---- view layer epilogue + rgb head ----------------------------------------------------------
+      {
+        mbar_wait(bar_acc(1), acc_cnt[1] & 1u);
+        ++acc_cnt[1];
+        tc_fence_after();
+        float c0 = aux_s[kAuxBRgb], c1 = aux_s[kAuxBRgb + 1], c2 = aux_s[kAuxBRgb + 2];
+#pragma unroll 1
+        for (int part = 0; part < 4; ++part) {
+          uint32_t v[32];
+          tmem_ld32(tmem_row + 256u + (uint32_t)part * 32u, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = part * 32 + j;
+            const float h = fmaxf(__uint_as_float(v[j]) + aux_s[kAuxBiasViews + col], 0.0f);
+            c0 = fmaf(h, aux_s[kAuxWRgb + col], c0);
+            c1 = fmaf(h, aux_s[kAuxWRgb + kWV + col], c1);
+            c2 = fmaf(h, aux_s[kAuxWRgb + 2 * kWV + col], c2);
+          }
+        }
+        tc_fence_before();
+        if (g < P.M) P.raw[g] = make_float4(c0, c1, c2, sigma);
+      }
+    }
+  }
+
+  // ---- teardown -----------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_mlp_tc(const MlpArgs& a, cudaStream_t s) {
+  const int64_t M = a.R * a.S;
+  if (M == 0) return 0;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    if (e != cudaSuccess) return set_error((int)e, "mlp_tc attr: %s", cudaGetErrorString(e));
+    attr_done[dev] = true;
+  }
+  TcParams P;
+  P.packed = reinterpret_cast<const uint8_t*>(a.packed);
+  P.rays_o = a.rays_o; P.rays_d = a.rays_d; P.viewdirs = a.viewdirs; P.z = a.z;
+  P.cond_proj = a.cond_proj; P.cond_index = a.cond_index; P.C = a.C;
+  P.raw = reinterpret_cast<float4*>(a.raw);
+  P.M = M; P.S = (int)a.S; P.ntiles = (M + kTileM - 1) / kTileM; P.cond = a.cond;
+  int64_t blocks = num_sms();
+  if (blocks > P.ntiles) blocks = P.ntiles;
+  k_mlp_tc<<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
+  return check_launch("mlp_tc");
+}
+
+}  // namespace fnerf

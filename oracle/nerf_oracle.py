@@ -36,22 +36,22 @@ COND_DIM = 256
 
 
 # --------------------------------------------------------------------------- A.1
+def _norm3(d: torch.Tensor) -> torch.Tensor:
+    """|d| with a pinned evaluation order, (x*x + y*y) + z*z in fp32, and a CORRECTLY ROUNDED square
+    root (evaluated in fp64, rounded once).  torch.sqrt on an AVX-512 CPU is 1 ulp off the IEEE
+    result in ~0.2 % of inputs (measured on the GPU box), so it cannot define a bit-exact contract;
+    CUDA's sqrt.rn.f32 is the IEEE result."""
+    n2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    return torch.sqrt(n2.double()).float()
+
+
 def ray_setup(rays_d: torch.Tensor):
     """viewdirs = d/|d|, dnorm = |d| (rays_d itself stays un-normalised)."""
-    dnorm = torch.sqrt((rays_d * rays_d).sum(-1))          # sum of three terms, left to right
-    viewdirs = rays_d / dnorm[:, None]
-    return viewdirs, dnorm
-
-
-def _norm3(d: torch.Tensor) -> torch.Tensor:
-    # explicit left-to-right evaluation so the kernel can reproduce it: (x*x + y*y) + z*z
-    return torch.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])
-
-
-def ray_setup_exact(rays_d: torch.Tensor):
-    """Same as ray_setup but with a pinned summation order (what the kernels implement)."""
     dnorm = _norm3(rays_d)
     return rays_d / dnorm[:, None], dnorm
+
+
+ray_setup_exact = ray_setup
 
 
 # --------------------------------------------------------------------------- A.2
@@ -171,7 +171,7 @@ def raw2outputs(raw: torch.Tensor, z: torch.Tensor, dnorm: torch.Tensor,
                 white_bkgd: bool = False, raw_noise: Optional[torch.Tensor] = None):
     """SURVEY.md A.5.  raw [R,S,4], z [R,S], dnorm [R] -> dict(rgb, disp, acc, depth, weights)."""
     dists = z[:, 1:] - z[:, :-1]
-    dists = torch.cat([dists, torch.full_like(dists[:, :1], 1e10)], -1)
+    dists = torch.cat([dists, torch.full_like(z[:, :1], 1e10)], -1)
     dists = dists * dnorm[:, None]
     rgb = torch.sigmoid(raw[..., :3])
     sigma = raw[..., 3]

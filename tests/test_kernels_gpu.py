@@ -1,0 +1,256 @@
+"""Stage-isolated parity of every C-ABI entry against the CPU oracle on identical inputs
+("Kernel unit parity").  All calls go through libfnerf.so via ctypes.
+
+Bars (BASELINE.json north_star): bit-exact sample positions and importance-bin indices;
+compositing <= 1e-5 abs in fp32; fp32 MLP <= 2e-5 abs on raw; bf16 MLP checked end to end in
+test_render_gpu.py."""
+import math
+
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F(cuda_device):
+    import fashion_nerf_b200 as f
+    f.load_library()
+    return f
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------ A.1
+def test_ray_setup_bit_exact(F, cuda_device):
+    _, d = O.pinhole_rays(37, 53)
+    d = torch.cat([d, torch.randn(1000, 3, generator=_gen(0)) * 3])
+    vd_ref, dn_ref = O.ray_setup_exact(d)
+    vd, dn = F.ops.ray_setup(d.to(cuda_device))
+    assert torch.equal(vd.cpu(), vd_ref) and torch.equal(dn.cpu(), dn_ref)
+
+
+# ------------------------------------------------------------------------------------------ A.2
+@pytest.mark.parametrize("R,N,jitter,lindisp", [(4096, 64, True, False), (4096, 64, False, False),
+                                                (1001, 256, True, False), (333, 7, True, True),
+                                                (5, 1, True, False), (64, 64, False, True)])
+def test_stratified_bit_exact(F, cuda_device, R, N, jitter, lindisp):
+    g = _gen(1)
+    near = 1.5 + torch.rand(R, generator=g)
+    far = 5.0 + torch.rand(R, generator=g) * 2
+    t = torch.linspace(0, 1, N)
+    u = torch.rand(R, N, generator=g) if jitter else None
+    ref = O.stratified(near, far, t, u, lindisp)
+    got = F.ops.stratified(near.to(cuda_device), far.to(cuda_device), t.to(cuda_device),
+                           None if u is None else u.to(cuda_device), lindisp)
+    assert torch.equal(got.cpu(), ref)
+
+
+def test_stratified_near_equals_far(F, cuda_device):
+    near = torch.full((8,), 3.0)
+    t = torch.linspace(0, 1, 16)
+    u = torch.rand(8, 16, generator=_gen(2))
+    ref = O.stratified(near, near, t, u)
+    got = F.ops.stratified(near.to(cuda_device), near.to(cuda_device), t.to(cuda_device), u.to(cuda_device))
+    assert torch.equal(got.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------ A.7
+def _coarse_case(R, Nc, seed, peaky=True):
+    g = _gen(seed)
+    near, far = torch.full((R,), 2.0), torch.full((R,), 6.0)
+    z = O.stratified(near, far, torch.linspace(0, 1, Nc), torch.rand(R, Nc, generator=g))
+    raw = torch.randn(R, Nc, 4, generator=g) * (4.0 if peaky else 1.0)
+    w = O.raw2outputs(raw, z, torch.ones(R))["weights"]
+    return z, w
+
+
+@pytest.mark.parametrize("R,Nc,Nf", [(4096, 64, 128), (513, 256, 768), (100, 17, 5), (64, 3, 1), (7, 64, 200)])
+def test_importance_bit_exact(F, cuda_device, R, Nc, Nf):
+    z, w = _coarse_case(R, Nc, 3)
+    u = torch.rand(R, Nf, generator=_gen(4))
+    ref = O.sample_pdf(z, w, u)
+    got = F.ops.importance(z.to(cuda_device), w.to(cuda_device), u.to(cuda_device))
+    assert torch.equal(got["inds"].cpu().long(), ref["inds"])
+    assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
+    assert torch.equal(got["z_f"].cpu(), ref["z_f"])
+    assert torch.allclose(got["z_std"].cpu(), ref["z_std"], rtol=1e-4, atol=1e-6)
+
+
+def test_importance_shared_linspace_row(F, cuda_device):
+    z, w = _coarse_case(777, 64, 5)
+    u1 = torch.linspace(0, 1, 128)
+    ref = O.sample_pdf(z, w, u1[None].expand(777, 128))
+    got = F.ops.importance(z.to(cuda_device), w.to(cuda_device), u1.to(cuda_device))
+    assert torch.equal(got["inds"].cpu().long(), ref["inds"])
+    assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
+    assert torch.equal(got["z_f"].cpu(), ref["z_f"])
+
+
+def test_importance_edge_cases(F, cuda_device):
+    """u in {0, just below 1, 1, > cdf[-1]}, all-zero weights, one-hot weights, constant z."""
+    Nc = 64
+    z = torch.linspace(2, 6, Nc)[None].repeat(4, 1).contiguous()
+    z[3] = 4.0                                                    # near == far
+    w = torch.zeros(4, Nc)
+    w[1, 30] = 1.0
+    w[2] = torch.rand(Nc, generator=_gen(6)) * 1e-7
+    u = torch.tensor([0.0, 1e-8, 0.25, 0.5, 0.99999994, 1.0, 1.0000001, 1.5])[None].repeat(4, 1).contiguous()
+    ref = O.sample_pdf(z, w, u)
+    got = F.ops.importance(z.to(cuda_device), w.to(cuda_device), u.to(cuda_device))
+    assert torch.equal(got["inds"].cpu().long(), ref["inds"])
+    assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
+    assert torch.equal(got["z_f"].cpu(), ref["z_f"])
+
+
+def test_importance_full_size_sortedness(F, cuda_device):
+    """Size-independent property at the long-ray size (cfg 4): output sorted, a permutation of inputs."""
+    R, Nc, Nf = 20000, 256, 768
+    g = torch.Generator(device="cpu").manual_seed(7)
+    z = torch.sort(torch.rand(R, Nc, generator=g) * 4 + 2, -1)[0].to(cuda_device)
+    w = torch.rand(R, Nc, generator=g).to(cuda_device)
+    u = torch.rand(R, Nf, generator=g).to(cuda_device)
+    got = F.ops.importance(z, w, u)
+    zf = got["z_f"]
+    assert (zf[:, 1:] >= zf[:, :-1]).all()
+    assert torch.equal(zf, torch.sort(torch.cat([z, got["z_samples"]], -1), -1)[0])
+    assert (got["inds"] >= 1).all() and (got["inds"] <= Nc - 1).all()
+
+
+# ------------------------------------------------------------------------------------------ A.3
+def test_posenc(F, cuda_device):
+    x = torch.rand(5000, 3, generator=_gen(8)) * 12 - 6
+    for L in (10, 4, 0):
+        ref = O.posenc(x, L) if L > 0 else x
+        got = F.ops.posenc(x.to(cuda_device), L).cpu()
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------ A.5
+@pytest.mark.parametrize("R,S,white,noise", [(4096, 64, False, False), (4096, 192, False, False),
+                                             (257, 1024, True, False), (1000, 33, True, True), (3, 1, False, False)])
+def test_composite_fwd(F, cuda_device, R, S, white, noise):
+    g = _gen(9)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0]
+    raw = torch.randn(R, S, 4, generator=g)
+    dn = 1 + torch.rand(R, generator=g)
+    nz = torch.randn(R, S, generator=g) if noise else None
+    ref = O.raw2outputs(raw, z, dn, white, nz)
+    got = F.ops.composite_fwd(raw.to(cuda_device), z.to(cuda_device), dn.to(cuda_device), white_bkgd=white,
+                              raw_noise=None if nz is None else nz.to(cuda_device))
+    for k in ("rgb", "acc", "weights"):
+        assert (got[k].cpu() - ref[k]).abs().max() <= 1e-5, k
+    assert (got["depth"].cpu() - ref["depth"]).abs().max() <= 1e-5 * 6       # depth = sum w*z, z <= 6
+    assert torch.allclose(got["disp"].cpu(), ref["disp"], rtol=1e-4, atol=1e-6, equal_nan=True)
+
+
+def test_composite_fwd_empty_space(F, cuda_device):
+    R, S = 64, 64
+    z = torch.linspace(2, 6, S)[None].repeat(R, 1).contiguous()
+    raw = -torch.rand(R, S, 4, generator=_gen(10))                    # sigma <= 0 everywhere
+    ref = O.raw2outputs(raw, z, torch.ones(R), True)
+    got = F.ops.composite_fwd(raw.to(cuda_device), z.to(cuda_device), torch.ones(R, device=cuda_device), white_bkgd=True)
+    assert torch.equal(got["weights"].cpu(), torch.zeros(R, S))
+    assert torch.equal(got["rgb"].cpu(), ref["rgb"])
+    assert torch.isnan(got["disp"]).all() and torch.isnan(ref["disp"]).all()
+
+
+def test_composite_fwd_constant_sigma_closed_form(F, cuda_device):
+    """Analytic check independent of the oracle: acc = 1, rgb = sigmoid(c) for constant raw."""
+    R, S = 128, 192
+    z = torch.linspace(2, 6, S)[None].repeat(R, 1).contiguous()
+    raw = torch.zeros(R, S, 4)
+    raw[..., 3] = 0.7
+    raw[..., :3] = torch.tensor([0.3, -0.2, 1.1])
+    got = F.ops.composite_fwd(raw.to(cuda_device), z.to(cuda_device), torch.ones(R, device=cuda_device))
+    assert (got["acc"].cpu() - 1).abs().max() < 1e-5
+    assert (got["rgb"].cpu() - torch.sigmoid(torch.tensor([0.3, -0.2, 1.1]))).abs().max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ A.6
+@pytest.mark.parametrize("R,S,white", [(1024, 64, False), (512, 192, True), (65, 1024, False), (9, 33, True)])
+def test_composite_bwd(F, cuda_device, R, S, white):
+    g = _gen(11)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0]
+    raw = torch.randn(R, S, 4, generator=g)
+    dn = 1 + torch.rand(R, generator=g)
+    g_rgb, g_d, g_a = torch.randn(R, 3, generator=g), torch.randn(R, generator=g), torch.randn(R, generator=g)
+    ref64 = O.composite_bwd(raw.double(), z.double(), dn.double(), g_rgb.double(), g_d.double(), g_a.double(), white)
+    ref32 = O.composite_bwd(raw, z, dn, g_rgb, g_d, g_a, white)
+    got = F.ops.composite_bwd(raw.to(cuda_device), z.to(cuda_device), dn.to(cuda_device), g_rgb.to(cuda_device),
+                              g_d.to(cuda_device), g_a.to(cuda_device), white_bkgd=white).cpu()
+    assert torch.isfinite(got).all()
+    err_kernel = (got.double() - ref64).abs().max().item()
+    err_oracle32 = (ref32.double() - ref64).abs().max().item()
+    scale = ref64.abs().max().item()
+    # the fp32 kernel must be as close to the fp64 truth as the fp32 oracle is (same conditioning)
+    assert err_kernel <= max(4 * err_oracle32, 1e-5 * max(scale, 1.0)), (err_kernel, err_oracle32, scale)
+
+
+# ------------------------------------------------------------------------------------------ weights
+@pytest.mark.parametrize("cond", [False, True])
+def test_pack_unpack_round_trip(F, cuda_device, cond):
+    sd = F.init_state_dict(3, cond)
+    flat = F.flatten_state_dict(sd, cond)
+    assert flat.numel() == F.ops.param_count(cond)
+    packed = F.ops.pack_weights(flat.to(cuda_device), cond)
+    back = F.ops.unpack_weights(packed, cond).cpu()
+    assert torch.equal(back, flat)
+
+
+def test_init_matches_oracle_init():
+    import fashion_nerf_b200 as f
+    a, b = f.init_state_dict(1), O.init_params(1)
+    assert all(torch.equal(a[k], b[k]) for k in b)
+
+
+# ------------------------------------------------------------------------------------------ A.4 fp32
+def _query_case(R, S, seed):
+    g = _gen(seed)
+    o = torch.rand(R, 3, generator=g) * 2 - 1
+    d = torch.randn(R, 3, generator=g)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0]
+    vd, _ = O.ray_setup_exact(d)
+    return o, d, vd, z
+
+
+@pytest.mark.parametrize("R,S", [(64, 64), (33, 7), (10, 192)])
+def test_mlp_fp32_vs_oracle(F, cuda_device, R, S):
+    p = O.init_params(0)
+    o, d, vd, z = _query_case(R, S, 12)
+    pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
+    ref = O.run_network(p, pts, vd)
+    net = F.NerfNetwork.from_state_dict(p, cuda_device)
+    got = F.ops.mlp_fwd(net.packed, o.to(cuda_device), d.to(cuda_device), vd.to(cuda_device), z.to(cuda_device),
+                        precision="fp32").cpu()
+    assert (got - ref).abs().max() <= 2e-5, (got - ref).abs().max()
+
+
+def test_mlp_fp32_cond_vs_oracle(F, cuda_device):
+    R, S, V = 48, 16, 4
+    p = O.init_params(2, cond=True)
+    o, d, vd, z = _query_case(R, S, 13)
+    cond = torch.randn(V, 256, generator=_gen(14))
+    view_id = torch.randint(0, V, (R,), generator=_gen(15))
+    pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
+    ref = O.run_network(p, pts, vd, cond[view_id])
+    net = F.NerfNetwork.from_state_dict(p, cuda_device, cond=True)
+    proj = F.ops.cond_project(net.packed, cond.to(cuda_device))
+    got = F.ops.mlp_fwd(net.packed, o.to(cuda_device), d.to(cuda_device), vd.to(cuda_device), z.to(cuda_device),
+                        precision="fp32", cond_proj=proj, cond_index=view_id.to(cuda_device)).cpu()
+    assert (got - ref).abs().max() <= 3e-5, (got - ref).abs().max()
+
+
+# ------------------------------------------------------------------------------------------ errors
+def test_error_codes_and_no_cpu_fallback(F, cuda_device):
+    lib = F.load_library()
+    assert lib.fnerf_stratified(None, None, None, None, None, 4, 4, 0, None) == -1
+    assert b"null" in lib.fnerf_last_error()
+    assert lib.fnerf_importance(None, None, None, 0, None, None, None, None, 4, 2, 4, None) == -2
+    with pytest.raises(F.FnerfError):
+        F.ops.ray_setup(torch.zeros(4, 3))                              # CPU tensor: rejected, not emulated
