@@ -35,6 +35,8 @@ class RenderArgs(ctypes.Structure):
         ("z_c", c_void_p), ("z_f", c_void_p), ("raw_c", c_void_p), ("raw_f", c_void_p),
         ("weights_c", c_void_p), ("weights_f", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("ev_coarse_start", c_void_p), ("ev_coarse_stop", c_void_p),
+        ("ev_fine_start", c_void_p), ("ev_fine_stop", c_void_p),
     ]
 
 

@@ -208,8 +208,10 @@ int fnerf_render_rays(const fnerf_render_args* a, fnerf_stream_t stream) {
   int rc;
   if ((rc = fnerf_ray_setup(a->rays_d, viewdirs, dnorm, R, stream))) return rc;
   if ((rc = fnerf_stratified(a->near, a->far, a->t_vals, a->u_strat, z_c, R, Nc, a->lindisp, stream))) return rc;
+  if (a->ev_coarse_start) cudaEventRecord((cudaEvent_t)a->ev_coarse_start, s);
   if ((rc = fnerf_mlp_fwd(a->precision, a->packed_coarse, a->cond, a->rays_o, a->rays_d, viewdirs, z_c,
                           a->cond_proj_coarse, a->cond_index, a->C, raw_c, R, Nc, stream))) return rc;
+  if (a->ev_coarse_stop) cudaEventRecord((cudaEvent_t)a->ev_coarse_stop, s);
   if (Nf == 0) {
     if ((rc = fnerf_composite_fwd(raw_c, z_c, dnorm, nullptr, a->rgb, a->depth, a->acc, a->disp, a->weights_c ? weights_c : nullptr,
                                   R, Nc, a->white_bkgd, stream))) return rc;
@@ -223,8 +225,10 @@ int fnerf_render_rays(const fnerf_render_args* a, fnerf_stream_t stream) {
                                 a->white_bkgd, stream))) return rc;
   if ((rc = fnerf_importance(z_c, weights_c, a->u_fine, a->u_fine_row_stride, z_samples, z_f, nullptr, a->z_std,
                              R, Nc, Nf, stream))) return rc;
+  if (a->ev_fine_start) cudaEventRecord((cudaEvent_t)a->ev_fine_start, s);
   if ((rc = fnerf_mlp_fwd(a->precision, a->packed_fine, a->cond, a->rays_o, a->rays_d, viewdirs, z_f,
                           a->cond_proj_fine, a->cond_index, a->C, raw_f, R, Nc + Nf, stream))) return rc;
+  if (a->ev_fine_stop) cudaEventRecord((cudaEvent_t)a->ev_fine_stop, s);
   if ((rc = fnerf_composite_fwd(raw_f, z_f, dnorm, nullptr, a->rgb, a->depth, a->acc, a->disp, a->weights_f, R,
                                 Nc + Nf, a->white_bkgd, stream))) return rc;
   return 0;

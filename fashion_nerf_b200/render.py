@@ -17,6 +17,15 @@ from .model import NerfModel
 
 _T = torch.Tensor
 _tvals_cache: Dict[tuple, torch.Tensor] = {}
+_profile_events = None
+
+
+def set_profile_events(events) -> None:
+    """Install (or clear with None) four already-recorded torch.cuda.Event(enable_timing=True) objects;
+    every following render_rays call records them around its coarse / fine network-query launches."""
+    global _profile_events
+    _profile_events = None if events is None else tuple(events)
+
 
 
 def _linspace01(n: int, device) -> torch.Tensor:
@@ -67,6 +76,8 @@ def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat,
         a.z_f, a.raw_f = z_f.data_ptr(), raw_f.data_ptr()
     a.weights_f = None
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    if _profile_events is not None:      # (coarse_start, coarse_stop, fine_start, fine_stop) torch.cuda.Event
+        a.ev_coarse_start, a.ev_coarse_stop, a.ev_fine_start, a.ev_fine_stop = [e.cuda_event for e in _profile_events]
     with torch.cuda.device(dev):
         _lib.check(lib.fnerf_render_rays(ctypes.byref(a), torch.cuda.current_stream().cuda_stream), "render_rays")
     return [rgb, disp, acc, depth, rgb0, disp0, acc0, z_std, z_c, z_f, raw_c, raw_f]
