@@ -1,19 +1,22 @@
 // Fused bf16 tensor-core network query (A.3 + A.4 + A.8) for sm_100a: tcgen05.mma with TMEM
 // accumulators, weights streamed by bulk TMA, activations resident in shared memory.
 //
-// One persistent CTA per SM walks 128-sample tiles.  Warp roles (192 threads):
+// One persistent CTA per SM walks 128-sample tiles.  Warp roles (576 threads):
 //   warp 0      weight producer: one lane streams the 39 pre-swizzled weight chunks of the network
 //               (layout.h section A, consumption order) through a ring of 32 KB stages with
 //               cp.async.bulk + mbarrier complete_tx;
 //   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=256|128, K=16) for every layer,
 //               A = activation / encoding tile in smem (K-major, 128B swizzle), B = weight stage,
 //               D = one of two 128x256 fp32 accumulators in TMEM (layer parity);
-//   warps 2..5  workers: build the positional-encoding tiles for their row (sample), and run the
-//               per-layer epilogue: tcgen05.ld 64 columns -> +bias (+hoisted cond projection)
-//               -> ReLU -> bf16 -> swizzled st.shared as the next layer's A operand.
-// The epilogue hands the activation tile over in 64-column K-blocks (one mbarrier each), so the
-// next layer's MMAs on K-block 0 start while the epilogue is still converting K-blocks 1..3; the
-// two TMEM accumulators make that overlap legal.  Encoded samples and activations never touch HBM:
+//   warps 2..17 workers, four groups of four warps (a warp's TMEM lane quadrant is warp%4, so each
+//               group covers the 128 rows): group 0 / 1 build the xyz / direction encoding tiles;
+//               all groups run the per-layer epilogue in 32-column units: tcgen05.ld -> +bias
+//               (+hoisted cond projection) -> ReLU -> bf16 -> swizzled st.shared as the next
+//               layer's A operand.  Group g converts units g and g+4 of the 8 units of a layer.
+// The epilogue hands the activation tile over in 64-column K-blocks (one mbarrier each, two units),
+// so the next layer's MMAs on K-blocks 0/1 start while K-blocks 2/3 are still being converted; the
+// two TMEM accumulators make that overlap legal.  (v1 of this kernel ran the epilogue on 4 warps:
+// ncu showed one latency-bound warp per scheduler, 880 cycles per K-block, tensor pipe 43 % busy.)  Encoded samples and activations never touch HBM:
 // per sample the kernel reads 4 B (z) and writes 16 B (raw).
 // sigma (256->1) and rgb (128->3) are fp32 dot products inside the epilogues of layer 7 and of the
 // view layer.
@@ -25,14 +28,16 @@ using namespace ptx;
 
 constexpr int kTileM = 128;
 constexpr int kStages = 3;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 576;
+constexpr int kWorkerThreads = 512;
 constexpr uint32_t kKBlockBytes = kTileM * 128;                 // 16 KB: 128 rows x 64 bf16
 constexpr uint32_t kOffAct = 0;                                 // 4 K-blocks
 constexpr uint32_t kOffPe = 4 * kKBlockBytes;                   // xyz encoding (63 -> 64)
 constexpr uint32_t kOffPed = kOffPe + kKBlockBytes;             // direction encoding (27 -> 32 used)
 constexpr uint32_t kOffW = kOffPed + kKBlockBytes;              // weight stages
 constexpr uint32_t kOffAux = kOffW + kStages * kBigChunkBytes;  // fp32 biases + heads
-constexpr uint32_t kOffBar = kOffAux + kAuxFloats * 4;
+constexpr uint32_t kOffPart = kOffAux + kAuxFloats * 4;        // head partials of groups 1..3: 3 x 128 float4
+constexpr uint32_t kOffBar = kOffPart + 3 * kTileM * 16;
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 1 + 2;
 constexpr uint32_t kTcSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;  // + tmem ptr + alignment slack
 static_assert(kOffBar % 8 == 0, "barrier alignment");
@@ -46,55 +51,54 @@ struct TcParams {
   int64_t M; int S; int64_t ntiles; int cond;
 };
 
-// epilogue of one 64-column K-block: TMEM -> (+bias, +rowbias) -> [ReLU] -> bf16 -> swizzled smem
+// epilogue of one 32-column unit: TMEM -> (+bias, +rowbias) -> [ReLU] -> bf16 -> swizzled smem.
+// `chunk0` is the index (0 or 4) of the unit's first 16-byte chunk inside its 128-byte K-block row.
 template <bool kRelu, bool kSigma, bool kCond>
-__device__ __forceinline__ void epilogue_kblock(uint32_t taddr, const float* __restrict__ bias_s,
-                                                const float* __restrict__ walpha_s,
-                                                const float* __restrict__ rowbias, uint32_t act_row_addr,
-                                                uint32_t row, float& sigma) {
-  uint32_t v0[32], v1[32];
-  tmem_ld32(taddr, v0);
-  tmem_ld32(taddr + 32, v1);
+__device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __restrict__ bias_s,
+                                              const float* __restrict__ walpha_s,
+                                              const float* __restrict__ rowbias, uint32_t act_row_addr,
+                                              uint32_t chunk0, uint32_t row, float& sigma) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
   tmem_ld_wait();
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int c = 0; c < 4; ++c) {            // 16-byte chunk = 8 columns
+    float x[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {          // 16-byte chunk = 8 columns
-      float x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(h == 0 ? v0[c * 8 + j] : v1[c * 8 + j]);
-      const int col = h * 32 + c * 8;
-      const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
-      const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 4);
-      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-      if (kCond) {
-        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rowbias + col));
-        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rowbias + col + 4));
-        x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-        x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
-      }
-      if (kSigma) {
-        const float4 w0 = *reinterpret_cast<const float4*>(walpha_s + col);
-        const float4 w1 = *reinterpret_cast<const float4*>(walpha_s + col + 4);
-        sigma = fmaf(fmaxf(x[0], 0.f), w0.x, sigma); sigma = fmaf(fmaxf(x[1], 0.f), w0.y, sigma);
-        sigma = fmaf(fmaxf(x[2], 0.f), w0.z, sigma); sigma = fmaf(fmaxf(x[3], 0.f), w0.w, sigma);
-        sigma = fmaf(fmaxf(x[4], 0.f), w1.x, sigma); sigma = fmaf(fmaxf(x[5], 0.f), w1.y, sigma);
-        sigma = fmaf(fmaxf(x[6], 0.f), w1.z, sigma); sigma = fmaf(fmaxf(x[7], 0.f), w1.w, sigma);
-      }
-      uint32_t p0, p1, p2, p3;
-      if (kRelu) {
-        p0 = pack_bf16_relu(x[0], x[1]); p1 = pack_bf16_relu(x[2], x[3]);
-        p2 = pack_bf16_relu(x[4], x[5]); p3 = pack_bf16_relu(x[6], x[7]);
-      } else {
-        p0 = pack_bf16(x[0], x[1]); p1 = pack_bf16(x[2], x[3]);
-        p2 = pack_bf16(x[4], x[5]); p3 = pack_bf16(x[6], x[7]);
-      }
-      const uint32_t c16 = (uint32_t)(h * 4 + c);
-      st_shared_v4(act_row_addr + ((c16 ^ (row & 7u)) << 4), p0, p1, p2, p3);
+    for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[c * 8 + j]);
+    const int col = c * 8;
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 4);
+    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    if (kCond) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(rowbias + col));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(rowbias + col + 4));
+      x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+      x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
     }
+    if (kSigma) {
+      const float4 w0 = *reinterpret_cast<const float4*>(walpha_s + col);
+      const float4 w1 = *reinterpret_cast<const float4*>(walpha_s + col + 4);
+      sigma = fmaf(fmaxf(x[0], 0.f), w0.x, sigma); sigma = fmaf(fmaxf(x[1], 0.f), w0.y, sigma);
+      sigma = fmaf(fmaxf(x[2], 0.f), w0.z, sigma); sigma = fmaf(fmaxf(x[3], 0.f), w0.w, sigma);
+      sigma = fmaf(fmaxf(x[4], 0.f), w1.x, sigma); sigma = fmaf(fmaxf(x[5], 0.f), w1.y, sigma);
+      sigma = fmaf(fmaxf(x[6], 0.f), w1.z, sigma); sigma = fmaf(fmaxf(x[7], 0.f), w1.w, sigma);
+    }
+    uint32_t p0, p1, p2, p3;
+    if (kRelu) {
+      p0 = pack_bf16_relu(x[0], x[1]); p1 = pack_bf16_relu(x[2], x[3]);
+      p2 = pack_bf16_relu(x[4], x[5]); p3 = pack_bf16_relu(x[6], x[7]);
+    } else {
+      p0 = pack_bf16(x[0], x[1]); p1 = pack_bf16(x[2], x[3]);
+      p2 = pack_bf16(x[4], x[5]); p3 = pack_bf16(x[6], x[7]);
+    }
+    const uint32_t c16 = chunk0 + (uint32_t)c;
+    st_shared_v4(act_row_addr + ((c16 ^ (row & 7u)) << 4), p0, p1, p2, p3);
   }
 }
+
+__device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -118,8 +122,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 128);
-    mbar_init(bar_pe, 128);
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 256);   // two worker groups per K-block
+    mbar_init(bar_pe, 256);                                       // encoding groups 0 and 1
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
     fence_barrier_init();
@@ -197,17 +201,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     }
   } else {
     // ================================ workers: encodings + epilogues ===============================
-    const uint32_t q = (uint32_t)warp & 3u;
+    const uint32_t q = (uint32_t)warp & 3u;                 // TMEM lane quadrant this warp may read
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;         // 0..3
     const uint32_t row = q * 32u + (uint32_t)lane;
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     uint32_t acc_cnt[2] = {0u, 0u};
     const uint32_t act_row = base + kOffAct + row * 128u;
+    float4* part_s = reinterpret_cast<float4*>(base_ptr + kOffPart);
     for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride) {
       const int64_t g = tile * kTileM + row;
       const int64_t gc = g < P.M ? g : P.M - 1;
       const int64_t ray = gc / P.S;
       // ---- positional encodings (A.3): sincos once, then double-angle recurrence per octave -----
-      {
+      if (grp == 0) {
         const float zv = P.z[gc];
         float f[64];
         f[63] = 0.0f;
@@ -232,6 +238,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           st_shared_v4(pe_row + (((uint32_t)c16 ^ (row & 7u)) << 4),
                        pack_bf16(f[c16 * 8 + 0], f[c16 * 8 + 1]), pack_bf16(f[c16 * 8 + 2], f[c16 * 8 + 3]),
                        pack_bf16(f[c16 * 8 + 4], f[c16 * 8 + 5]), pack_bf16(f[c16 * 8 + 6], f[c16 * 8 + 7]));
+        fence_proxy_async_smem();
+        mbar_arrive(bar_pe);
+      } else if (grp == 1) {
         float d[32];
 #pragma unroll
         for (int i = kPED; i < 32; ++i) d[i] = 0.0f;
@@ -256,16 +265,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4),
                        pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
                        pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
+        fence_proxy_async_smem();
+        mbar_arrive(bar_pe);
       }
-      fence_proxy_async_smem();
-      mbar_arrive(bar_pe);
 
       const float* rowbias = nullptr;
       if (P.cond) {
         const int64_t crow = P.cond_index ? (int64_t)P.cond_index[ray] : (P.C == 1 ? 0 : ray);
         rowbias = P.cond_proj + crow * kW;
       }
-      float sigma = aux_s[kAuxBAlpha];
+      float sigma = 0.0f;                                   // this thread's share of the sigma head
       // ---- trunk + feature epilogues ---------------------------------------------------------------
 #pragma unroll 1
       for (int step = 0; step < 9; ++step) {
@@ -276,43 +285,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         const float* bias_s = aux_s + (step < 8 ? kAuxBiasPts + step * 256 : kAuxBiasFeat);
         const uint32_t tacc = tmem_row + (uint32_t)a * 256u;
 #pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint32_t dst = act_row + (uint32_t)kb * kKBlockBytes;
+        for (int round = 0; round < 2; ++round) {
+          const uint32_t unit = grp + 4u * (uint32_t)round;  // 32-column unit 0..7
+          const uint32_t kb = unit >> 1, half = unit & 1u;
+          const uint32_t col0 = unit * 32u;
+          const uint32_t dst = act_row + kb * kKBlockBytes;
           if (step == 8)
-            epilogue_kblock<false, false, false>(tacc + kb * 64, bias_s + kb * 64, nullptr, nullptr, dst, row, sigma);
+            epilogue_unit<false, false, false>(tacc + col0, bias_s + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
           else if (step == 7)
-            epilogue_kblock<true, true, false>(tacc + kb * 64, bias_s + kb * 64, aux_s + kAuxWAlpha + kb * 64, nullptr, dst, row, sigma);
+            epilogue_unit<true, true, false>(tacc + col0, bias_s + col0, aux_s + kAuxWAlpha + col0, nullptr, dst, half * 4u, row, sigma);
           else if (step == 5 && P.cond)
-            epilogue_kblock<true, false, true>(tacc + kb * 64, bias_s + kb * 64, nullptr, rowbias + kb * 64, dst, row, sigma);
+            epilogue_unit<true, false, true>(tacc + col0, bias_s + col0, nullptr, rowbias + col0, dst, half * 4u, row, sigma);
           else
-            epilogue_kblock<true, false, false>(tacc + kb * 64, bias_s + kb * 64, nullptr, nullptr, dst, row, sigma);
+            epilogue_unit<true, false, false>(tacc + col0, bias_s + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(bar_act(kb));
         }
       }
-      // ---- view layer epilogue + rgb head ----------------------------------------------------------
+      // ---- view layer epilogue + rgb head: each group reduces 32 of the 128 columns ---------------
       {
         mbar_wait(bar_acc(1), acc_cnt[1] & 1u);
         ++acc_cnt[1];
         tc_fence_after();
-        float c0 = aux_s[kAuxBRgb], c1 = aux_s[kAuxBRgb + 1], c2 = aux_s[kAuxBRgb + 2];
-#pragma unroll 1
-        for (int part = 0; part < 4; ++part) {
-          uint32_t v[32];
-          tmem_ld32(tmem_row + 256u + (uint32_t)part * 32u, v);
-          tmem_ld_wait();
+        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+        uint32_t v[32];
+        tmem_ld32(tmem_row + 256u + grp * 32u, v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = part * 32 + j;
-            const float h = fmaxf(__uint_as_float(v[j]) + aux_s[kAuxBiasViews + col], 0.0f);
-            c0 = fmaf(h, aux_s[kAuxWRgb + col], c0);
-            c1 = fmaf(h, aux_s[kAuxWRgb + kWV + col], c1);
-            c2 = fmaf(h, aux_s[kAuxWRgb + 2 * kWV + col], c2);
-          }
+        for (int j = 0; j < 32; ++j) {
+          const int col = (int)grp * 32 + j;
+          const float h = fmaxf(__uint_as_float(v[j]) + aux_s[kAuxBiasViews + col], 0.0f);
+          c0 = fmaf(h, aux_s[kAuxWRgb + col], c0);
+          c1 = fmaf(h, aux_s[kAuxWRgb + kWV + col], c1);
+          c2 = fmaf(h, aux_s[kAuxWRgb + 2 * kWV + col], c2);
         }
         tc_fence_before();
-        if (g < P.M) P.raw[g] = make_float4(c0, c1, c2, sigma);
+        if (grp != 0) part_s[(grp - 1u) * kTileM + row] = make_float4(c0, c1, c2, sigma);
+        worker_bar_sync();
+        if (grp == 0) {
+          const float4 p1 = part_s[row], p2 = part_s[kTileM + row], p3 = part_s[2 * kTileM + row];
+          c0 = aux_s[kAuxBRgb] + ((c0 + p1.x) + (p2.x + p3.x));
+          c1 = aux_s[kAuxBRgb + 1] + ((c1 + p1.y) + (p2.y + p3.y));
+          c2 = aux_s[kAuxBRgb + 2] + ((c2 + p1.z) + (p2.z + p3.z));
+          const float sg = aux_s[kAuxBAlpha] + ((sigma + p1.w) + (p2.w + p3.w));
+          if (g < P.M) P.raw[g] = make_float4(c0, c1, c2, sg);
+        }
       }
     }
   }
