@@ -27,21 +27,55 @@ namespace fnerf {
 using namespace ptx;
 
 constexpr int kTileM = 128;
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kTcThreads = 576;
 constexpr int kWorkerThreads = 512;
 constexpr uint32_t kKBlockBytes = kTileM * 128;                 // 16 KB: 128 rows x 64 bf16
 constexpr uint32_t kOffAct = 0;                                 // 4 K-blocks
 constexpr uint32_t kOffPe = 4 * kKBlockBytes;                   // xyz encoding (63 -> 64)
-constexpr uint32_t kOffPed = kOffPe + kKBlockBytes;             // direction encoding (27 -> 32 used)
-constexpr uint32_t kOffW = kOffPed + kKBlockBytes;              // weight stages
+// The direction encoding (27 -> 32 columns used) shares the xyz-encoding buffer: layer 5 is the last
+// reader of the xyz tile, the view layer the only reader of the direction tile, so group 1 drops its
+// rows in after layer 5's accumulator is complete.  The 16 KB saved buy the 4th weight stage (the
+// L2 -> smem bulk latency is ~1000 cycles, i.e. >= 64 KB must be in flight to sustain 64 B/clk).
+constexpr uint32_t kOffPed = kOffPe;
+constexpr uint32_t kOffW = kOffPe + kKBlockBytes;               // weight stages
 constexpr uint32_t kOffAux = kOffW + kStages * kBigChunkBytes;  // fp32 biases + heads
-constexpr uint32_t kOffPart = kOffAux + kAuxFloats * 4;        // head partials of groups 1..3: 3 x 128 float4
-constexpr uint32_t kOffBar = kOffPart + 3 * kTileM * 16;
+constexpr uint32_t kOffBar = kOffAux + kAuxFloats * 4;
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 1 + 2;
 constexpr uint32_t kTcSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;  // + tmem ptr + alignment slack
 static_assert(kOffBar % 8 == 0, "barrier alignment");
 static_assert(kTcSmemBytes <= 227 * 1024, "shared memory budget");
+
+// Optional timeline tracer (compile with -DFNERF_TRACE, see tools/trace_tc.py): CTA 0 stamps clock64()
+// at pipeline events of its 3rd tile into a global buffer.  Compiled out of the product library.
+#ifdef FNERF_TRACE
+__device__ long long* g_trace_buf = nullptr;
+#define FN_TRACE(cond, slot) do { if (blockIdx.x == 0 && (cond) && g_trace_buf) g_trace_buf[(slot)] = clock64(); } while (0)
+#else
+#define FN_TRACE(cond, slot) do { } while (0)
+#endif
+
+// The MMA schedule of one tile: chunk c of the packed weight stream (layout.h) against which A tile.
+struct MmaChunk {
+  int a_sel;       // 0 = activation K-block `kb`, 1 = encoding buffer (xyz tile, or direction tile for the view layer)
+  int kb;          // activation K-block (also the act-ready barrier to honour when `gated`)
+  int ksteps;      // K=16 MMAs in this chunk
+  int n128;        // 1: N = 128 (view layer), 0: N = 256
+  int acc;         // TMEM accumulator 0 / 1
+  int fresh;       // first MMA overwrites the accumulator
+  int gated;       // wait for the epilogue's act-ready[kb]
+  int commit_acc;  // last chunk of a layer: commit to acc-full[acc]
+};
+__host__ __device__ constexpr MmaChunk mma_chunk(int c) {
+  if (c == 0) return {1, 0, 4, 0, 0, 1, 0, 1};                                                              // L0
+  if (c <= 16) return {0, (c - 1) % 4, 4, 0, (1 + (c - 1) / 4) & 1, (c - 1) % 4 == 0, 1, (c - 1) % 4 == 3};  // L1..L4
+  if (c == 17) return {1, 0, 4, 0, 1, 1, 0, 0};                                                             // L5 xyz block
+  if (c <= 21) return {0, c - 18, 4, 0, 1, 0, 1, c - 18 == 3};                                              // L5 trunk block
+  if (c <= 29) return {0, (c - 22) % 4, 4, 0, (6 + (c - 22) / 4) & 1, (c - 22) % 4 == 0, 1, (c - 22) % 4 == 3};  // L6, L7
+  if (c <= 33) return {0, c - 30, 4, 0, 0, c - 30 == 0, 1, c - 30 == 3};                                    // feature
+  if (c <= 37) return {0, c - 34, 4, 1, 1, c - 34 == 0, 1, 0};                                              // views, trunk block
+  return {1, 0, 2, 1, 1, 0, 0, 1};                                                                          // views, direction block
+}
 
 struct TcParams {
   const uint8_t* packed;
@@ -57,18 +91,25 @@ template <bool kRelu, bool kSigma, bool kCond>
 __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __restrict__ bias_s,
                                               const float* __restrict__ walpha_s,
                                               const float* __restrict__ rowbias, uint32_t act_row_addr,
-                                              uint32_t chunk0, uint32_t row, float& sigma) {
+                                              uint32_t chunk0, uint32_t row, float& sigma,
+                                              long long* tr = nullptr) {
   uint32_t v[32];
+  if (tr) tr[0] = clock64();
   tmem_ld32(taddr, v);
   tmem_ld_wait();
+  if (tr) tr[1] = clock64();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {            // 16-byte chunk = 8 columns
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[c * 8 + j]);
     const int col = c * 8;
+#ifdef EXP_NOBIAS
+    const float4 b0 = make_float4(0.1f, 0.2f, 0.3f, 0.4f), b1 = b0;
+#else
     const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
     const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 4);
+#endif
     x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
     x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
     if (kCond) {
@@ -94,7 +135,11 @@ __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __res
       p2 = pack_bf16(x[4], x[5]); p3 = pack_bf16(x[6], x[7]);
     }
     const uint32_t c16 = chunk0 + (uint32_t)c;
+#ifdef EXP_NOSTS
+    if (p0 == 0x12345678u)
+#endif
     st_shared_v4(act_row_addr + ((c16 ^ (row & 7u)) << 4), p0, p1, p2, p3);
+    if (tr) tr[2 + c] = clock64();
   }
 }
 
@@ -122,8 +167,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+#ifdef EXP_WARP_ARRIVE
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 8);
+#else
     for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 256);   // two worker groups per K-block
-    mbar_init(bar_pe, 256);                                       // encoding groups 0 and 1
+#endif
+    mbar_init(bar_pe, 128);                                       // encoding group 0
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
     fence_barrier_init();
@@ -153,50 +202,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ===================================================
+    // The issuing lane must stay ahead of the tensor pipe: one 64-wide K chunk is 4 MMAs = 512 pipe
+    // cycles (N=256).  A timeline trace of the first version showed ~850 issue-side cycles per chunk
+    // (two serial mbarrier probes at ~150 cycles each, descriptor rebuilds, ~100 cycles per MMA), i.e.
+    // the issuer, not the pipe, paced the kernel.  Hence: the chunk schedule is a compile-time table
+    // (fully unrolled), descriptors advance by 64-bit adds, and the barriers of chunk c+1 are probed
+    // (non-blocking test_wait) before chunk c's MMAs are issued so the probe latency hides behind them.
     if (lane == 0) {
       constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256);
       constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
       uint32_t wc = 0, act_cnt = 0, tile_cnt = 0;
-      // consume one weight stage against `ksteps` K=16 slices of the A tile at a_addr
-      auto issue_chunk = [&](uint32_t a_addr, int ksteps, uint32_t idesc, uint32_t tmem_d, bool first) {
-        const uint32_t s = wc % kStages;
-        mbar_wait(bar_full(s), (wc / kStages) & 1u);
-        tc_fence_after();
-        const uint32_t b_addr = base + kOffW + s * kBigChunkBytes;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_bf16(tmem_d, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc,
-                    (first && ks == 0) ? 0u : 1u);
-        umma_commit(bar_empty(s));
-        ++wc;
-      };
-      // a 256-wide layer whose A operand is the activation tile, gated per K-block by the epilogue
-      auto trunk_layer = [&](uint32_t tmem_d, uint32_t idesc, bool first_is_fresh) {
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(bar_act(kb), act_cnt & 1u);
-          tc_fence_after();
-          issue_chunk(base + kOffAct + kb * kKBlockBytes, 4, idesc, tmem_d, first_is_fresh && kb == 0);
-        }
-        ++act_cnt;
-      };
-      const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256;
+      uint32_t tslot = 0;   // tracer: slots [0,256): (before waits, operands ready, issued) per chunk
+      const uint64_t desc_act = umma_desc_sw128(base + kOffAct);
+      const uint64_t desc_pe = umma_desc_sw128(base + kOffPe);      // also the direction tile (shared buffer)
+      const uint64_t desc_w = umma_desc_sw128(base + kOffW);
+      const uint32_t acc_addr[2] = {tmem_base, tmem_base + 256};
       for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride, ++tile_cnt) {
         mbar_wait(bar_pe, tile_cnt & 1u);
-        tc_fence_after();
-        issue_chunk(base + kOffPe, 4, idesc256, acc0, true);                    // L0
-        umma_commit(bar_acc(0));
-        for (int l = 1; l <= 4; ++l) {                                          // L1..L4
-          trunk_layer((l & 1) ? acc1 : acc0, idesc256, true);
-          umma_commit(bar_acc(l & 1));
+        bool w_ready = mbar_test_wait(bar_full(wc % kStages), (wc / kStages) & 1u);
+        bool a_ready = true;
+#pragma unroll
+        for (int c = 0; c < kNumChunks; ++c) {
+          const MmaChunk op = mma_chunk(c);
+          const uint32_t s = wc % kStages;
+          FN_TRACE(tile_cnt == 2, tslot++);
+          if (op.gated && !a_ready) mbar_wait(bar_act(op.kb), act_cnt & 1u);
+          if (!w_ready) mbar_wait(bar_full(s), (wc / kStages) & 1u);
+          tc_fence_after();
+          FN_TRACE(tile_cnt == 2, tslot++);
+          // probe the next chunk's barriers now; the answers are needed only after this chunk is issued
+          const uint32_t act_next = act_cnt + ((op.gated && op.kb == 3) ? 1u : 0u);
+          w_ready = mbar_test_wait(bar_full((wc + 1) % kStages), ((wc + 1) / kStages) & 1u);
+          if (c + 1 < kNumChunks) {
+            const MmaChunk nx = mma_chunk(c + 1);
+            a_ready = nx.gated ? mbar_test_wait(bar_act(nx.kb), act_next & 1u) : true;
+          } else {
+            a_ready = true;
+          }
+          const uint64_t a_desc = (op.a_sel == 0 ? desc_act + (uint64_t)(op.kb * (kKBlockBytes >> 4)) : desc_pe);
+          const uint64_t b_desc = desc_w + (uint64_t)(s * (kBigChunkBytes >> 4));
+          const uint32_t idesc = op.n128 ? idesc128 : idesc256;
+#pragma unroll
+          for (int ks = 0; ks < op.ksteps; ++ks)
+            umma_bf16(acc_addr[op.acc], a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
+                      (op.fresh && ks == 0) ? 0u : 1u);
+          umma_commit(bar_empty(s));
+          if (op.commit_acc) umma_commit(bar_acc(op.acc));
+          FN_TRACE(tile_cnt == 2, tslot++);
+          act_cnt = act_next;
+          ++wc;
         }
-        issue_chunk(base + kOffPe, 4, idesc256, acc1, true);                    // L5: encoding block
-        trunk_layer(acc1, idesc256, false);                                     //     + trunk block
-        umma_commit(bar_acc(1));
-        trunk_layer(acc0, idesc256, true);  umma_commit(bar_acc(0));            // L6
-        trunk_layer(acc1, idesc256, true);  umma_commit(bar_acc(1));            // L7
-        trunk_layer(acc0, idesc256, true);  umma_commit(bar_acc(0));            // feature
-        trunk_layer(acc1, idesc128, true);                                      // views: feature block
-        issue_chunk(base + kOffPed, 2, idesc128, acc1, false);                  //        + direction block
-        umma_commit(bar_acc(1));
       }
     }
   } else {
@@ -206,8 +261,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     const uint32_t row = q * 32u + (uint32_t)lane;
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     uint32_t acc_cnt[2] = {0u, 0u};
+    uint32_t wtile = 0, wslot = 256 + grp * 64;   // tracer: per group 64 slots from 256 (lane 0 of quadrant-0 warp)
     const uint32_t act_row = base + kOffAct + row * 128u;
-    float4* part_s = reinterpret_cast<float4*>(base_ptr + kOffPart);
+    uint32_t ped_pk[16];                                    // group 1: packed direction encoding of this row
     for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride) {
       const int64_t g = tile * kTileM + row;
       const int64_t gc = g < P.M ? g : P.M - 1;
@@ -259,14 +315,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
             sn = s2;
           }
         }
-        const uint32_t ped_row = base + kOffPed + row * 128u;
 #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16)
-          st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4),
-                       pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
-                       pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
-        fence_proxy_async_smem();
-        mbar_arrive(bar_pe);
+        for (int i = 0; i < 16; ++i) ped_pk[i] = pack_bf16(d[2 * i], d[2 * i + 1]);   // stored after layer 5
       }
 
       const float* rowbias = nullptr;
@@ -279,9 +329,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
 #pragma unroll 1
       for (int step = 0; step < 9; ++step) {
         const int a = step & 1;
+        FN_TRACE(wtile == 2 && row == 0, wslot++);
         mbar_wait(bar_acc(a), acc_cnt[a] & 1u);
+        FN_TRACE(wtile == 2 && row == 0, wslot++);
         ++acc_cnt[a];
         tc_fence_after();
+        if (step == 5 && grp == 1) {        // layer 5's MMAs are complete: the xyz tile is dead, reuse it
+          const uint32_t ped_row = base + kOffPed + row * 128u;
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16)
+            st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4), ped_pk[4 * c16], ped_pk[4 * c16 + 1],
+                         ped_pk[4 * c16 + 2], ped_pk[4 * c16 + 3]);
+        }                                   // (made visible by the fence before this thread's next arrive)
         const float* bias_s = aux_s + (step < 8 ? kAuxBiasPts + step * 256 : kAuxBiasFeat);
         const uint32_t tacc = tmem_row + (uint32_t)a * 256u;
 #pragma unroll 1
@@ -298,9 +357,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
             epilogue_unit<true, false, true>(tacc + col0, bias_s + col0, nullptr, rowbias + col0, dst, half * 4u, row, sigma);
           else
             epilogue_unit<true, false, false>(tacc + col0, bias_s + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
+#ifdef FNERF_TRACE
+          long long* tr = (blockIdx.x == 0 && wtile == 2 && row == 0 && g_trace_buf && step == 2) ? g_trace_buf + 512 + grp * 32 + round * 16 : nullptr;
+          if (tr) tr[0] = clock64();
+#endif
+#ifndef EXP_NOFENCE
           fence_proxy_async_smem();
+#endif
+#ifdef FNERF_TRACE
+          if (tr) tr[1] = clock64();
+#endif
           tc_fence_before();
+#ifdef FNERF_TRACE
+          if (tr) tr[2] = clock64();
+#endif
+#ifdef EXP_WARP_ARRIVE
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_act(kb));
+#else
           mbar_arrive(bar_act(kb));
+#endif
+#ifdef FNERF_TRACE
+          if (tr) tr[3] = clock64();
+#endif
+          FN_TRACE(wtile == 2 && row == 0, wslot++);
         }
       }
       // ---- view layer epilogue + rgb head: each group reduces 32 of the 128 columns ---------------
@@ -321,10 +401,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           c2 = fmaf(h, aux_s[kAuxWRgb + 2 * kWV + col], c2);
         }
         tc_fence_before();
-        if (grp != 0) part_s[(grp - 1u) * kTileM + row] = make_float4(c0, c1, c2, sigma);
+        // partials of groups 1..3 park in the unused upper half (logical chunks 5..7) of this row of
+        // the encoding buffer; the view layer's MMAs (its only async-proxy reader) are complete
+        uint8_t* enc_row = base_ptr + kOffPe + row * 128u;
+        if (grp != 0) *reinterpret_cast<float4*>(enc_row + (((4u + grp) ^ (row & 7u)) << 4)) = make_float4(c0, c1, c2, sigma);
         worker_bar_sync();
         if (grp == 0) {
-          const float4 p1 = part_s[row], p2 = part_s[kTileM + row], p3 = part_s[2 * kTileM + row];
+          const float4 p1 = *reinterpret_cast<const float4*>(enc_row + ((5u ^ (row & 7u)) << 4));
+          const float4 p2 = *reinterpret_cast<const float4*>(enc_row + ((6u ^ (row & 7u)) << 4));
+          const float4 p3 = *reinterpret_cast<const float4*>(enc_row + ((7u ^ (row & 7u)) << 4));
           c0 = aux_s[kAuxBRgb] + ((c0 + p1.x) + (p2.x + p3.x));
           c1 = aux_s[kAuxBRgb + 1] + ((c1 + p1.y) + (p2.y + p3.y));
           c2 = aux_s[kAuxBRgb + 2] + ((c2 + p1.z) + (p2.z + p3.z));
@@ -332,6 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           if (g < P.M) P.raw[g] = make_float4(c0, c1, c2, sg);
         }
       }
+      ++wtile;
     }
   }
 
@@ -343,6 +429,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+#ifdef FNERF_TRACE
+extern "C" int fnerf_debug_set_trace(long long* buf) {
+  return (int)cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf));
+}
+#endif
 
 int launch_mlp_tc(const MlpArgs& a, cudaStream_t s) {
   const int64_t M = a.R * a.S;

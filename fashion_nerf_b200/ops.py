@@ -135,21 +135,23 @@ def mlp_fwd(packed: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, vi
 
 
 def mlp_bwd(packed: torch.Tensor, rays_o, rays_d, viewdirs, z, g_raw: torch.Tensor, flat_grad: torch.Tensor, *,
-            precision: str = "fp32", cond_proj=None, cond_index=None) -> torch.Tensor:
-    """Accumulates dL/dparams into flat_grad (flat layout) given g_raw[R,S,4]."""
+            precision: str = "fp32", cond_rows=None, cond_index=None) -> torch.Tensor:
+    """Accumulates dL/dparams into flat_grad (flat layout) given g_raw[R,S,4].  cond_rows: RAW codes [C,256]."""
     rays_o, rays_d, viewdirs, z, g_raw = (_f32(rays_o, "rays_o"), _f32(rays_d, "rays_d"),
                                           _f32(viewdirs, "viewdirs"), _f32(z, "z"), _f32(g_raw, "g_raw"))
     R, S = z.shape
     lib = _lib.load()
     ws_bytes = int(lib.fnerf_mlp_bwd_workspace_bytes(R, S))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-    has_cond = cond_proj is not None
-    C = cond_proj.shape[0] if has_cond else 0
+    has_cond = cond_rows is not None
+    if has_cond:
+        cond_rows = _f32(cond_rows, "cond_rows").reshape(-1, 256)
+    C = cond_rows.shape[0] if has_cond else 0
     if cond_index is not None:
         cond_index = cond_index.to(torch.int32).contiguous()
     with torch.cuda.device(z.device):
         check(lib.fnerf_mlp_bwd(PRECISIONS[precision], packed.data_ptr(), int(has_cond), rays_o.data_ptr(),
-                                rays_d.data_ptr(), viewdirs.data_ptr(), z.data_ptr(), _ptr(cond_proj),
+                                rays_d.data_ptr(), viewdirs.data_ptr(), z.data_ptr(), _ptr(cond_rows),
                                 _ptr(cond_index), C, g_raw.data_ptr(), flat_grad.data_ptr(), ws.data_ptr(), ws_bytes,
                                 R, S, _stream()), "mlp_bwd")
     return flat_grad

@@ -86,16 +86,17 @@ def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat,
 @torch.library.custom_op("fnerf::render_rays", mutates_args=())
 def render_rays_op(flat_c: _T, flat_f: _T, packed_c: _T, packed_f: _T, rays_o: _T, rays_d: _T, near: _T, far: _T,
                    t_vals: _T, u_strat: Optional[_T], u_fine: Optional[_T], cond_proj_c: Optional[_T],
-                   cond_proj_f: Optional[_T], cond_index: Optional[_T], n_importance: int, white_bkgd: bool,
-                   lindisp: bool, precision: int) -> List[_T]:
-    # flat_c / flat_f only anchor the autograd graph; the kernels read the packed blobs.
+                   cond_proj_f: Optional[_T], cond_index: Optional[_T], cond_rows: Optional[_T], n_importance: int,
+                   white_bkgd: bool, lindisp: bool, precision: int) -> List[_T]:
+    # flat_c / flat_f only anchor the autograd graph (and cond_rows only feeds the backward); the
+    # forward kernels read the packed blobs and the hoisted projections.
     return _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c,
                         cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision)
 
 
 @render_rays_op.register_fake
 def _(flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c,
-      cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision):
+      cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision):
     R, Nc, S = rays_o.shape[0], t_vals.numel(), t_vals.numel() + n_importance
     e = rays_o.new_empty
     zf, rf = (e(R, S), e(R, S, 4)) if n_importance > 0 else (e(0), e(0))
@@ -104,10 +105,9 @@ def _(flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_s
 
 def _setup_context(ctx, inputs, output):
     (flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c,
-     cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision) = inputs
+     cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision) = inputs
     z_c, z_f, raw_c, raw_f = output[8], output[9], output[10], output[11]
-    ctx.save_for_backward(packed_c, packed_f, rays_o, rays_d, z_c, z_f, raw_c, raw_f, cond_proj_c, cond_proj_f,
-                          cond_index)
+    ctx.save_for_backward(packed_c, packed_f, rays_o, rays_d, z_c, z_f, raw_c, raw_f, cond_rows, cond_index)
     ctx.n_importance, ctx.white_bkgd, ctx.precision = n_importance, white_bkgd, precision
     ctx.n_c, ctx.n_f = flat_c.numel(), flat_f.numel()
 
@@ -115,14 +115,14 @@ def _setup_context(ctx, inputs, output):
 def _backward(ctx, grads):
     """A.6 + MLP backward for the training loss (grads w.r.t. rgb/acc/depth maps; disp and z_std carry
     none in A.10).  Sample positions are detached (A.7)."""
-    packed_c, packed_f, rays_o, rays_d, z_c, z_f, raw_c, raw_f, cpc, cpf, cidx = ctx.saved_tensors
+    packed_c, packed_f, rays_o, rays_d, z_c, z_f, raw_c, raw_f, cond_rows, cidx = ctx.saved_tensors
     g_rgb, _g_disp, g_acc, g_depth, g_rgb0, _g_disp0, g_acc0 = grads[:7]
     viewdirs, dnorm = ops.ray_setup(rays_d)
     R = rays_o.shape[0]
     dev = rays_o.device
     zeros3 = None
 
-    def grad_net(packed, z, raw, gr, gd, ga, n_params, cp):
+    def grad_net(packed, z, raw, gr, gd, ga, n_params):
         nonlocal zeros3
         if gr is None and gd is None and ga is None:
             return None
@@ -131,16 +131,16 @@ def _backward(ctx, grads):
             gr = zeros3
         g_raw = ops.composite_bwd(raw, z, dnorm, gr.contiguous(), gd, ga, white_bkgd=ctx.white_bkgd)
         flat_grad = torch.zeros(n_params, dtype=torch.float32, device=dev)
-        ops.mlp_bwd(packed, rays_o, rays_d, viewdirs, z, g_raw, flat_grad, cond_proj=cp, cond_index=cidx)
+        ops.mlp_bwd(packed, rays_o, rays_d, viewdirs, z, g_raw, flat_grad, cond_rows=cond_rows, cond_index=cidx)
         return flat_grad
 
     if ctx.n_importance > 0:
-        g_flat_f = grad_net(packed_f, z_f, raw_f, g_rgb, g_depth, g_acc, ctx.n_f, cpf)
-        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb0, None, g_acc0, ctx.n_c, cpc)
+        g_flat_f = grad_net(packed_f, z_f, raw_f, g_rgb, g_depth, g_acc, ctx.n_f)
+        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb0, None, g_acc0, ctx.n_c)
     else:
         g_flat_f = None
-        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb, g_depth, g_acc, ctx.n_c, cpc)
-    return (g_flat_c, g_flat_f) + (None,) * 16
+        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb, g_depth, g_acc, ctx.n_c)
+    return (g_flat_c, g_flat_f) + (None,) * 17
 
 
 render_rays_op.register_autograd(_backward, setup_context=_setup_context)
@@ -204,7 +204,8 @@ def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, ne
         raise ValueError("model expects cond")
     outs = render_rays_op(model.coarse.flat, model.fine.flat, model.coarse.packed, model.fine.packed, rays_o, rays_d,
                           near_t, far_t, t_vals, u_strat, u_fine if N_importance > 0 else None, cpc, cpf, cidx,
-                          int(N_importance), bool(white_bkgd), bool(lindisp), ops.PRECISIONS[precision])
+                          cond if cond is not None else None, int(N_importance), bool(white_bkgd), bool(lindisp),
+                          ops.PRECISIONS[precision])
     n = len(_OUT_NAMES) if return_taps else 8
     return {k: v for k, v in zip(_OUT_NAMES[:n], outs[:n])}
 

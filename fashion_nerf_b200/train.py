@@ -1,0 +1,100 @@
+"""Data-parallel training step: render_rays forward, loss = mse(rgb, tgt) +
+mse(rgb0, tgt), backward through compositing (A.6) and the MLP, ONE all-reduce over the flat fp32
+gradient buffer of both networks (1,191,688 floats = 4.77 MB), Adam on the fp32 master parameters,
+re-pack of the kernel blobs.  One process per GPU; ``torch.distributed`` (NCCL over NVLink on the
+B200 box, gloo in the CPU tests) is used for nothing but that all-reduce.
+
+The host-side pieces (`allreduce_mean_`, `FlatAdam`) are plain torch so the world_size>1 logic is
+testable on CPU; the gradient computation itself has no CPU path."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from .model import NerfModel
+from .render import render_rays
+
+
+def allreduce_mean_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place average of the flat gradient buffer over the process group (no-op when not initialised)."""
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+            flat_grad.div_(world)
+    return flat_grad
+
+
+class FlatAdam:
+    """Adam (torch defaults: betas 0.9/0.999, eps 1e-8; A.10) over one flat fp32 parameter buffer."""
+
+    def __init__(self, n: int, device, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.lr, self.b1, self.b2, self.eps = lr, betas[0], betas[1], eps
+        self.m = torch.zeros(n, dtype=torch.float32, device=device)
+        self.v = torch.zeros(n, dtype=torch.float32, device=device)
+        self.t = 0
+
+    @torch.no_grad()
+    def step(self, params: torch.Tensor, grad: torch.Tensor) -> None:
+        """One Adam step over the whole buffer."""
+        self.t += 1
+        self.apply(params, grad, 0)
+
+    @torch.no_grad()
+    def apply(self, params: torch.Tensor, grad: torch.Tensor, offset: int) -> None:
+        """Update `params` (a view of the flat buffer starting at `offset`) at the current step count."""
+        n = params.numel()
+        m, v = self.m[offset:offset + n], self.v[offset:offset + n]
+        m.mul_(self.b1).add_(grad, alpha=1 - self.b1)
+        v.mul_(self.b2).addcmul_(grad, grad, value=1 - self.b2)
+        bc1, bc2 = 1 - self.b1 ** self.t, 1 - self.b2 ** self.t
+        denom = (v / bc2).sqrt_().add_(self.eps)
+        params.addcdiv_(m, denom, value=-self.lr / bc1)
+
+
+class Trainer:
+    """Holds the optimizer state of a NerfModel and runs data-parallel steps."""
+
+    def __init__(self, model: NerfModel, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, group=None):
+        self.model, self.group = model, group
+        self.n_c, self.n_f = model.coarse.flat.numel(), model.fine.flat.numel()
+        self.shared = model.fine is model.coarse
+        n = self.n_c if self.shared else self.n_c + self.n_f
+        self.opt = FlatAdam(n, model.device, lr, betas, eps)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=model.device)   # the all-reduce buffer
+
+    def step(self, rays_o: torch.Tensor, rays_d: torch.Tensor, target: torch.Tensor, near, far, N_samples: int,
+             N_importance: int, cond: Optional[torch.Tensor] = None, *, view_id=None, u_strat=None, u_fine=None,
+             white_bkgd: bool = False, precision: str = "bf16") -> Dict[str, torch.Tensor]:
+        m = self.model
+        fc = m.coarse.flat.detach().requires_grad_(True)
+        ff = fc if self.shared else m.fine.flat.detach().requires_grad_(True)
+        m.coarse.flat, m.fine.flat = fc, ff
+        out = render_rays(m, rays_o, rays_d, near, far, N_samples, N_importance, cond, view_id=view_id,
+                          u_strat=u_strat, u_fine=u_fine, white_bkgd=white_bkgd, precision=precision)
+        loss_f = ((out["rgb"] - target) ** 2).mean()
+        loss = loss_f + ((out["rgb0"] - target) ** 2).mean() if N_importance > 0 else loss_f
+        loss.backward()
+        with torch.no_grad():
+            g = self.flat_grad
+            g[:self.n_c].copy_(fc.grad)
+            if not self.shared:
+                if ff.grad is not None:
+                    g[self.n_c:].copy_(ff.grad)
+                else:
+                    g[self.n_c:].zero_()
+            allreduce_mean_(g, self.group)
+            m.coarse.flat, m.fine.flat = fc.detach(), ff.detach()
+            self.opt.t += 1
+            self.opt.apply(m.coarse.flat, g[:self.n_c], 0)
+            if not self.shared:
+                self.opt.apply(m.fine.flat, g[self.n_c:], self.n_c)
+            m.repack()
+        return {"loss": loss.detach(), "psnr": -10.0 * torch.log10(loss_f.detach())}
+
+
+def psnr_from_mse(mse: float) -> float:
+    return -10.0 * math.log10(max(mse, 1e-20))

@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(192, 1) k(const uint8_t* blob, int iters, long
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[8];
   __shared__ uint32_t tslot;
+  __shared__ int done;
+  if (threadIdx.x == 0) done = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1); fence_barrier_init(); }
   if (warp == 1) tmem_alloc(smem_u32(&tslot), 512);
@@ -35,6 +37,7 @@ __global__ void __launch_bounds__(192, 1) k(const uint8_t* blob, int iters, long
     mbar_wait(smem_u32(&bars[((iters - 1) & 1) ? 5 : 0]), ((iters - 1) >> 1) & 1);
     t1 = clock64();
     out[blockIdx.x] = t1 - t0;
+    *(volatile int*)&done = 1;
   } else if (warp == 0 && lane == 0 && TMA) {
     // stream 16 KB chunks as fast as allowed: 4 stages, wait for own completion only
     const int total = iters * 8;   // 8 x 16 KB per 16 MMAs(N=256) == the MLP's 64 B/clk at full rate
@@ -47,10 +50,15 @@ __global__ void __launch_bounds__(192, 1) k(const uint8_t* blob, int iters, long
     for (int s = 0; s < 4; ++s) mbar_wait(smem_u32(&bars[1 + s]), (((total - 4 + s) >> 2)) & 1);
   } else if (warp >= 2 && STS) {
     // epilogue-like traffic: each thread writes 64 x 16 B per "layer" (64 KB per CTA per iteration)
+    // run until the MMA thread is done; count 16-byte stores per thread
     const uint32_t row = (warp - 2) * 32 + lane;
-    for (int it = 0; it < iters; ++it)
+    long long n = 0;
+    while (*(volatile int*)&done == 0) {
       for (int c = 0; c < 32; ++c)
-        st_shared_v4(w_addr + 65536 + row * 128 + (((c & 7) ^ (row & 7)) << 4) + (c >> 3) * 0, it, c, row, 0);
+        st_shared_v4(w_addr + 65536 + row * 128 + (((c & 7) ^ (row & 7)) << 4), (uint32_t)n, c, row, 0);
+      n += 32;
+    }
+    if (lane == 0 && warp == 2) out[148 + blockIdx.x] = n;
   }
   tc_fence_before(); __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
@@ -69,8 +77,9 @@ void run(const uint8_t* blob, long long* out, const char* tag) {
   cudaEventRecord(e1);
   cudaError_t err = cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
-  long long h[148]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
-  double cyc = 0; for (int i = 0; i < 148; ++i) cyc += h[i]; cyc /= 148;
+  long long h[296]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+  double cyc = 0, sts = 0; for (int i = 0; i < 148; ++i) { cyc += h[i]; sts += h[148 + i]; } cyc /= 148; sts /= 148;
+  if (STS) printf("   sts: %.1f B/clk/SM from 4 warps (128 threads x 16 B x %.0f stores / %.0f cycles)\n", sts * 128 * 16 / cyc, sts, cyc);
   double flops = 148.0 * iters * 16 * 2.0 * 128 * N * 16;
   printf("{\"bench\":\"%s\",\"N\":%d,\"tma\":%d,\"sts\":%d,\"ms\":%.3f,\"TFLOPs\":%.1f,\"cycles_per_mma\":%.1f,\"err\":\"%s\"}\n", tag, N, (int)TMA, (int)STS, ms,
          flops / ms / 1e9, cyc / (iters * 16.0), cudaGetErrorString(err));
@@ -79,11 +88,12 @@ void run(const uint8_t* blob, long long* out, const char* tag) {
 int main() {
   uint8_t* blob; long long* out;
   cudaMalloc(&blob, 64 * 16384); cudaMemset(blob, 0, 64 * 16384);
-  cudaMalloc(&out, 148 * 8);
+  cudaMalloc(&out, 296 * 8); cudaMemset(out, 0, 296 * 8);
   run<256, false, false>(blob, out, "mma_only");
   run<128, false, false>(blob, out, "mma_only");
   run<256, true, false>(blob, out, "mma+tma");
   run<128, true, false>(blob, out, "mma+tma");
+  run<256, false, true>(blob, out, "mma+sts");
   run<256, true, true>(blob, out, "mma+tma+sts");
   run<128, true, true>(blob, out, "mma+tma+sts");
   return 0;
