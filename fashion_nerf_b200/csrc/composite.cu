@@ -110,6 +110,78 @@ k_composite_fwd(const float4* __restrict__ raw, const float* __restrict__ z,
   }
 }
 
+// Register-resident variant for S <= 32*NB (NB <= 8): every load of the ray is issued before the first
+// scan step (NB float4 + NB floats in flight per lane), which is what an HBM-bound kernel needs; the
+// software-pipelined kernel above keeps only one 32-sample block in flight per warp.
+template <int NB>
+__global__ void __launch_bounds__(kCompWarps * 32)
+k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
+                    const float* __restrict__ dnorm, float* __restrict__ rgb_out,
+                    float* __restrict__ depth_out, float* __restrict__ acc_out,
+                    float* __restrict__ disp_out, float* __restrict__ weights, int64_t R, int S, int white) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  const int64_t warp_stride = (int64_t)gridDim.x * kCompWarps;
+  for (int64_t r = warp_global; r < R; r += warp_stride) {
+    const float4* rawr = raw + r * S;
+    const float* zr = z + r * S;
+    float4 rv[NB];
+    float zv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = b * 32 + lane;
+      rv[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      zv[b] = 0.f;
+      if (i < S) { rv[b] = ldg_stream4(rawr + i); zv[b] = ldg_stream(zr + i); }
+    }
+    const float dn = dnorm[r];
+    float carry = 1.0f, a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = b * 32 + lane;
+      if (b * 32 < S) {                         // warp-uniform
+        float z_up = __shfl_down_sync(0xffffffffu, zv[b], 1);
+        const float z_first_next = (b + 1 < NB) ? __shfl_sync(0xffffffffu, zv[(b + 1 < NB) ? b + 1 : b], 0) : 0.f;
+        if (lane == 31) z_up = z_first_next;
+        const bool valid = i < S;
+        float dist = (i == S - 1) ? 1e10f : (z_up - zv[b]);
+        dist *= dn;
+        const float alpha = valid ? (1.0f - expf(-fmaxf(rv[b].w, 0.0f) * dist)) : 0.0f;
+        float p = valid ? (1.0f - alpha + 1e-10f) : 1.0f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_up_sync(0xffffffffu, p, o);
+          if (lane >= o) p *= n;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, p, 1);
+        if (lane == 0) excl = 1.0f;
+        const float w = alpha * (carry * excl);
+        carry *= __shfl_sync(0xffffffffu, p, 31);
+        if (valid) {
+          a_r += w * sigmoidf_(rv[b].x);
+          a_g += w * sigmoidf_(rv[b].y);
+          a_b += w * sigmoidf_(rv[b].z);
+          a_d += w * zv[b];
+          a_w += w;
+          if (weights != nullptr) weights[r * S + i] = w;
+        }
+      }
+    }
+    a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);
+    a_d = warp_sum(a_d); a_w = warp_sum(a_w);
+    if (lane == 0) {
+      const float bg = white ? (1.0f - a_w) : 0.0f;
+      rgb_out[3 * r] = a_r + bg;
+      rgb_out[3 * r + 1] = a_g + bg;
+      rgb_out[3 * r + 2] = a_b + bg;
+      depth_out[r] = a_d;
+      acc_out[r] = a_w;
+      const float q = a_d / a_w;
+      disp_out[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
+    }
+  }
+}
+
 int launch_composite_fwd(const float* raw, const float* z, const float* dnorm, const float* noise,
                          float* rgb, float* depth, float* acc, float* disp, float* weights,
                          int64_t R, int64_t S, int white, cudaStream_t s) {
@@ -117,6 +189,18 @@ int launch_composite_fwd(const float* raw, const float* z, const float* dnorm, c
   int64_t blocks = (R + kCompWarps - 1) / kCompWarps;
   const int64_t cap = (int64_t)num_sms() * 8 * 4;   // 8 resident CTAs/SM x 4 waves, grid-stride beyond
   if (blocks > cap) blocks = cap;
+  if (noise == nullptr && S <= 256) {
+    const float4* raw4 = (const float4*)raw;
+    const unsigned g = (unsigned)blocks, t = kCompWarps * 32;
+    switch ((S + 31) / 32) {
+      case 1: k_composite_fwd_reg<1><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      case 2: k_composite_fwd_reg<2><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      case 3: case 4: k_composite_fwd_reg<4><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      case 5: case 6: k_composite_fwd_reg<6><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      default: k_composite_fwd_reg<8><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+    }
+    return check_launch("composite_fwd");
+  }
   if (noise != nullptr)
     k_composite_fwd<true><<<(unsigned)blocks, kCompWarps * 32, 0, s>>>(
         (const float4*)raw, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white);
