@@ -45,27 +45,44 @@ FN_HD int64_t flat_count(int cond) { return flat_weight_offset(kNumLayers, cond)
 // ---- packed blob -----------------------------------------------------------------------------
 // Section A: bf16 UMMA chunk stream, consumption order.  A chunk is ROWS x 64 bf16, K-major,
 // 128-byte swizzle (byte (r, c16) at r*128 + ((c16 ^ (r & 7)) << 4)), i.e. the exact shared-memory
-// image one bulk-TMA copy drops into a pipeline stage.
-//   chunk 0        : L0   [256 x 64]  cols 0..62 = W0, col 63 = 0
-//   chunks 1..16   : L1..L4, 4 K-chunks each
-//   chunk 17       : L5 positional block W5[:,0:63] (+ zero col)
-//   chunks 18..21  : L5 trunk block W5[:, hoff + 64*kb ..], hoff = 63 (+256 when cond)
-//   chunks 22..29  : L6, L7
-//   chunks 30..33  : feature_linear
-//   chunks 34..37  : views_linears.0 trunk block [128 x 64] each (16 KB)
-//   chunk 38       : views_linears.0 direction block [128 x 64], cols 0..26 = Wv[:,256:283]
+// image one bulk-TMA copy drops into a pipeline stage.  Chunk kinds (chunk_desc):
+//   TRUNK  W[:, base + 64*kb ..]                      A operand = activation K-block kb
+//   XYZ    W[:, 0:63] (+ zero column)                 A operand = xyz-encoding tile      (layers 0, 5)
+//   BIAS   zeros except col 27 = bf16(b), col 28 = bf16(b - bf16(b))
+//                                                     A operand = K-step 1 (cols 16..31) of the
+//          direction-encoding tile, whose cols 27, 28 hold 1.0 -> the fp32 accumulator receives the
+//          bias to ~16 mantissa bits and the epilogue needs no bias add
+//   DIR    Wv[:, 256:283] in cols 0..26, view-layer bias hi/lo in cols 27, 28 (view layer only)
+// Order: L0 {XYZ,BIAS}; L1..L4 {k0..k3,BIAS}; L5 {XYZ,k0..k3,BIAS}; L6,L7 {k0..k3,BIAS};
+// feature {k0..k3,BIAS}; views {k0..k3 (128 rows), DIR (128 rows)}.
 constexpr int kChunkK = 64;
-constexpr int kBigChunks = 34;
+constexpr int kBigChunks = 43;
 constexpr int kSmallChunks = 5;
 constexpr int kNumChunks = kBigChunks + kSmallChunks;
 constexpr int kBigChunkBytes = 256 * kChunkK * 2;   // 32768
 constexpr int kSmallChunkBytes = 128 * kChunkK * 2; // 16384
+constexpr int kBiasColHi = 27, kBiasColLo = 28;     // inside the direction tile / BIAS and DIR chunks
 constexpr int64_t kSecABytes = (int64_t)kBigChunks * kBigChunkBytes + (int64_t)kSmallChunks * kSmallChunkBytes;
 FN_HD int64_t chunk_offset(int c) {
   return c < kBigChunks ? (int64_t)c * kBigChunkBytes
                         : (int64_t)kBigChunks * kBigChunkBytes + (int64_t)(c - kBigChunks) * kSmallChunkBytes;
 }
 FN_HD int chunk_bytes(int c) { return c < kBigChunks ? kBigChunkBytes : kSmallChunkBytes; }
+
+enum { CHUNK_TRUNK = 0, CHUNK_XYZ = 1, CHUNK_BIAS = 2, CHUNK_DIR = 3 };
+struct ChunkDesc { int layer; int kind; int kb; };   // layer = flat layer id (0..7 trunk, 9 feature, 10 views)
+FN_HD constexpr ChunkDesc chunk_desc(int c) {
+  if (c == 0) return {0, CHUNK_XYZ, 0};
+  if (c == 1) return {0, CHUNK_BIAS, 0};
+  if (c <= 21) return {1 + (c - 2) / 5, (c - 2) % 5 == 4 ? CHUNK_BIAS : CHUNK_TRUNK, (c - 2) % 5};
+  if (c == 22) return {5, CHUNK_XYZ, 0};
+  if (c <= 26) return {5, CHUNK_TRUNK, c - 23};
+  if (c == 27) return {5, CHUNK_BIAS, 0};
+  if (c <= 37) return {6 + (c - 28) / 5, (c - 28) % 5 == 4 ? CHUNK_BIAS : CHUNK_TRUNK, (c - 28) % 5};
+  if (c <= 42) return {9, c - 38 == 4 ? CHUNK_BIAS : CHUNK_TRUNK, c - 38};
+  if (c <= 46) return {10, CHUNK_TRUNK, c - 43};
+  return {10, CHUNK_DIR, 0};
+}
 
 // Section B: fp32 "aux" (biases and the two tiny heads), offsets in floats.
 constexpr int kAuxBiasPts = 0;        // 8 x 256

@@ -2,7 +2,7 @@
 // accumulators, weights streamed by bulk TMA, activations resident in shared memory.
 //
 // One persistent CTA per SM walks 128-sample tiles.  Warp roles (576 threads):
-//   warp 0      weight producer: one lane streams the 39 pre-swizzled weight chunks of the network
+//   warp 0      weight producer: one lane streams the 48 pre-swizzled weight chunks of the network
 //               (layout.h section A, consumption order) through a ring of 32 KB stages with
 //               cp.async.bulk + mbarrier complete_tx;
 //   warp 1      MMA issuer: one lane issues tcgen05.mma (M=128, N=256|128, K=16) for every layer,
@@ -10,16 +10,24 @@
 //               D = one of two 128x256 fp32 accumulators in TMEM (layer parity);
 //   warps 2..17 workers, four groups of four warps (a warp's TMEM lane quadrant is warp%4, so each
 //               group covers the 128 rows): group 0 / 1 build the xyz / direction encoding tiles;
-//               all groups run the per-layer epilogue in 32-column units: tcgen05.ld -> +bias
-//               (+hoisted cond projection) -> ReLU -> bf16 -> swizzled st.shared as the next
-//               layer's A operand.  Group g converts units g and g+4 of the 8 units of a layer.
+//               all groups run the per-layer epilogue in 32-column units: tcgen05.ld -> ReLU -> bf16
+//               -> swizzled st.shared as the next layer's A operand.  Group g converts units g and
+//               g+4 of the 8 units of a layer.
 // The epilogue hands the activation tile over in 64-column K-blocks (one mbarrier each, two units),
 // so the next layer's MMAs on K-blocks 0/1 start while K-blocks 2/3 are still being converted; the
-// two TMEM accumulators make that overlap legal.  (v1 of this kernel ran the epilogue on 4 warps:
-// ncu showed one latency-bound warp per scheduler, 880 cycles per K-block, tensor pipe 43 % busy.)  Encoded samples and activations never touch HBM:
-// per sample the kernel reads 4 B (z) and writes 16 B (raw).
-// sigma (256->1) and rgb (128->3) are fp32 dot products inside the epilogues of layer 7 and of the
-// view layer.
+// two TMEM accumulators make that overlap legal.
+//
+// Biases ride in the GEMM: the direction-encoding tile carries 1.0 in its two spare columns (27, 28)
+// and every layer ends with one extra K=16 MMA of that tile's K-step 1 against a BIAS chunk holding
+// bf16(b) and bf16(b - bf16(b)) in those columns (zeros elsewhere), so the fp32 accumulator already
+// contains the bias (to ~16 mantissa bits) and the epilogue is a single F2FP.RELU per two elements.
+// History (profiles/r1_microbench.md): 4 epilogue warps -> 43 % tensor-pipe (one latency-bound warp
+// per scheduler); 16 warps with an fp32 bias add -> 48-52 % (FADD + F2FP issue bound, ~2250 cycles
+// per layer against 2048 MMA cycles).
+//
+// Encoded samples and activations never touch HBM: per sample the kernel reads 4 B (z) and writes
+// 16 B (raw).  sigma (256->1) and rgb (128->3) are fp32 dot products inside the epilogues of layer 7
+// and of the view layer.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -27,20 +35,17 @@ namespace fnerf {
 using namespace ptx;
 
 constexpr int kTileM = 128;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kTcThreads = 576;
 constexpr int kWorkerThreads = 512;
 constexpr uint32_t kKBlockBytes = kTileM * 128;                 // 16 KB: 128 rows x 64 bf16
 constexpr uint32_t kOffAct = 0;                                 // 4 K-blocks
 constexpr uint32_t kOffPe = 4 * kKBlockBytes;                   // xyz encoding (63 -> 64)
-// The direction encoding (27 -> 32 columns used) shares the xyz-encoding buffer: layer 5 is the last
-// reader of the xyz tile, the view layer the only reader of the direction tile, so group 1 drops its
-// rows in after layer 5's accumulator is complete.  The 16 KB saved buy the 4th weight stage (the
-// L2 -> smem bulk latency is ~1000 cycles, i.e. >= 64 KB must be in flight to sustain 64 B/clk).
-constexpr uint32_t kOffPed = kOffPe;
-constexpr uint32_t kOffW = kOffPe + kKBlockBytes;               // weight stages
-constexpr uint32_t kOffAux = kOffW + kStages * kBigChunkBytes;  // fp32 biases + heads
-constexpr uint32_t kOffBar = kOffAux + kAuxFloats * 4;
+constexpr uint32_t kOffPed = kOffPe + kKBlockBytes;             // direction encoding (27) + ones (cols 27, 28)
+constexpr uint32_t kOffW = kOffPed + kKBlockBytes;              // weight stages
+constexpr uint32_t kOffHeads = kOffW + kStages * kBigChunkBytes;  // fp32 head weights (aux from kAuxWAlpha on)
+constexpr int kHeadFloats = kAuxFloats - kAuxWAlpha;
+constexpr uint32_t kOffBar = kOffHeads + kHeadFloats * 4;
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 1 + 2;
 constexpr uint32_t kTcSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;  // + tmem ptr + alignment slack
 static_assert(kOffBar % 8 == 0, "barrier alignment");
@@ -55,26 +60,28 @@ __device__ long long* g_trace_buf = nullptr;
 #define FN_TRACE(cond, slot) do { } while (0)
 #endif
 
-// The MMA schedule of one tile: chunk c of the packed weight stream (layout.h) against which A tile.
+// The MMA schedule of one tile, derived from the packed chunk order (layout.h chunk_desc).
 struct MmaChunk {
-  int a_sel;       // 0 = activation K-block `kb`, 1 = encoding buffer (xyz tile, or direction tile for the view layer)
+  int a_sel;       // 0 = activation K-block kb, 1 = xyz tile, 2 = direction tile
   int kb;          // activation K-block (also the act-ready barrier to honour when `gated`)
-  int ksteps;      // K=16 MMAs in this chunk
+  int kstep0;      // first K=16 step inside the A tile / weight chunk
+  int ksteps;      // number of K=16 MMAs
   int n128;        // 1: N = 128 (view layer), 0: N = 256
   int acc;         // TMEM accumulator 0 / 1
   int fresh;       // first MMA overwrites the accumulator
   int gated;       // wait for the epilogue's act-ready[kb]
   int commit_acc;  // last chunk of a layer: commit to acc-full[acc]
 };
+__host__ __device__ constexpr int layer_step(int flat_layer) { return flat_layer < 8 ? flat_layer : (flat_layer == 9 ? 8 : 9); }
 __host__ __device__ constexpr MmaChunk mma_chunk(int c) {
-  if (c == 0) return {1, 0, 4, 0, 0, 1, 0, 1};                                                              // L0
-  if (c <= 16) return {0, (c - 1) % 4, 4, 0, (1 + (c - 1) / 4) & 1, (c - 1) % 4 == 0, 1, (c - 1) % 4 == 3};  // L1..L4
-  if (c == 17) return {1, 0, 4, 0, 1, 1, 0, 0};                                                             // L5 xyz block
-  if (c <= 21) return {0, c - 18, 4, 0, 1, 0, 1, c - 18 == 3};                                              // L5 trunk block
-  if (c <= 29) return {0, (c - 22) % 4, 4, 0, (6 + (c - 22) / 4) & 1, (c - 22) % 4 == 0, 1, (c - 22) % 4 == 3};  // L6, L7
-  if (c <= 33) return {0, c - 30, 4, 0, 0, c - 30 == 0, 1, c - 30 == 3};                                    // feature
-  if (c <= 37) return {0, c - 34, 4, 1, 1, c - 34 == 0, 1, 0};                                              // views, trunk block
-  return {1, 0, 2, 1, 1, 0, 0, 1};                                                                          // views, direction block
+  const ChunkDesc d = chunk_desc(c);
+  const int acc = layer_step(d.layer) & 1;
+  const bool first = c == 0 || chunk_desc(c - 1).layer != d.layer;
+  const bool last = c == kNumChunks - 1 || chunk_desc(c + 1).layer != d.layer;
+  if (d.kind == CHUNK_TRUNK) return {0, d.kb, 0, 4, d.layer == 10, acc, first, 1, last};
+  if (d.kind == CHUNK_XYZ) return {1, 0, 0, 4, 0, acc, first, 0, last};
+  if (d.kind == CHUNK_BIAS) return {2, 0, 1, 1, 0, acc, first, 0, last};     // K-step 1 = cols 16..31 (ones at 27, 28)
+  return {2, 0, 0, 2, 1, acc, first, 0, last};                              // CHUNK_DIR: cols 0..31
 }
 
 struct TcParams {
@@ -85,33 +92,22 @@ struct TcParams {
   int64_t M; int S; int64_t ntiles; int cond;
 };
 
-// epilogue of one 32-column unit: TMEM -> (+bias, +rowbias) -> [ReLU] -> bf16 -> swizzled smem.
-// `chunk0` is the index (0 or 4) of the unit's first 16-byte chunk inside its 128-byte K-block row.
+// epilogue of one 32-column unit: TMEM -> (+rowbias) -> [ReLU] -> bf16 -> swizzled smem.  The layer
+// bias is already in the accumulator.  `chunk0` is the index (0 or 4) of the unit's first 16-byte
+// chunk inside its 128-byte K-block row.
 template <bool kRelu, bool kSigma, bool kCond>
-__device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __restrict__ bias_s,
-                                              const float* __restrict__ walpha_s,
+__device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __restrict__ walpha_s,
                                               const float* __restrict__ rowbias, uint32_t act_row_addr,
-                                              uint32_t chunk0, uint32_t row, float& sigma,
-                                              long long* tr = nullptr) {
+                                              uint32_t chunk0, uint32_t row, float& sigma) {
   uint32_t v[32];
-  if (tr) tr[0] = clock64();
   tmem_ld32(taddr, v);
   tmem_ld_wait();
-  if (tr) tr[1] = clock64();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {            // 16-byte chunk = 8 columns
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[c * 8 + j]);
     const int col = c * 8;
-#ifdef EXP_NOBIAS
-    const float4 b0 = make_float4(0.1f, 0.2f, 0.3f, 0.4f), b1 = b0;
-#else
-    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col + 4);
-#endif
-    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
     if (kCond) {
       const float4 r0 = __ldg(reinterpret_cast<const float4*>(rowbias + col));
       const float4 r1 = __ldg(reinterpret_cast<const float4*>(rowbias + col + 4));
@@ -135,11 +131,7 @@ __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __res
       p2 = pack_bf16(x[4], x[5]); p3 = pack_bf16(x[6], x[7]);
     }
     const uint32_t c16 = chunk0 + (uint32_t)c;
-#ifdef EXP_NOSTS
-    if (p0 == 0x12345678u)
-#endif
     st_shared_v4(act_row_addr + ((c16 ^ (row & 7u)) << 4), p0, p1, p2, p3);
-    if (tr) tr[2 + c] = clock64();
   }
 }
 
@@ -156,23 +148,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   const uint32_t bar_pe = bar0 + 8u * (2 * kStages + 4);
   auto bar_acc = [&](int a) { return bar0 + 8u * (2 * kStages + 5 + a); };
   const uint32_t tmem_slot = bar0 + 8u * kNumBars;
-  float* aux_s = reinterpret_cast<float*>(base_ptr + kOffAux);
+  float* heads_s = reinterpret_cast<float*>(base_ptr + kOffHeads);   // index with (kAux* - kAuxWAlpha)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time setup ---------------------------------------------------------------------------
   {
-    const float* aux_g = reinterpret_cast<const float*>(P.packed + kSecBOffset);
-    for (int i = threadIdx.x; i < kAuxFloats; i += kTcThreads) aux_s[i] = aux_g[i];
+    const float* aux_g = reinterpret_cast<const float*>(P.packed + kSecBOffset) + kAuxWAlpha;
+    for (int i = threadIdx.x; i < kHeadFloats; i += kTcThreads) heads_s[i] = aux_g[i];
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-#ifdef EXP_WARP_ARRIVE
-    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 8);
-#else
     for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 256);   // two worker groups per K-block
-#endif
-    mbar_init(bar_pe, 128);                                       // encoding group 0
+    mbar_init(bar_pe, 256);                                       // encoding groups 0 and 1
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
     fence_barrier_init();
@@ -208,47 +196,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     // the issuer, not the pipe, paced the kernel.  Hence: the chunk schedule is a compile-time table
     // (fully unrolled), descriptors advance by 64-bit adds, and the barriers of chunk c+1 are probed
     // (non-blocking test_wait) before chunk c's MMAs are issued so the probe latency hides behind them.
-    if (lane == 0) {
+    // The loop runs warp-uniformly on all 32 lanes and only the MMA / commit instructions are
+    // predicated on one elected lane: with a divergent `if (lane == 0)` around the loop ptxas cannot
+    // prove the descriptors uniform and wraps EVERY tcgen05.mma in an elect/R2UR waterfall loop.
+    {
       constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256);
       constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
       uint32_t wc = 0, act_cnt = 0, tile_cnt = 0;
-      uint32_t tslot = 0;   // tracer: slots [0,256): (before waits, operands ready, issued) per chunk
+      [[maybe_unused]] uint32_t tslot = 0;   // tracer: slots [0,256): (before waits, operands ready, issued) per chunk
       const uint64_t desc_act = umma_desc_sw128(base + kOffAct);
-      const uint64_t desc_pe = umma_desc_sw128(base + kOffPe);      // also the direction tile (shared buffer)
+      const uint64_t desc_pe = umma_desc_sw128(base + kOffPe);
+      const uint64_t desc_ped = umma_desc_sw128(base + kOffPed);
       const uint64_t desc_w = umma_desc_sw128(base + kOffW);
-      const uint32_t acc_addr[2] = {tmem_base, tmem_base + 256};
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
+      const uint32_t acc_addr[2] = {tmem_u, tmem_u + 256};
       for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride, ++tile_cnt) {
         mbar_wait(bar_pe, tile_cnt & 1u);
-        bool w_ready = mbar_test_wait(bar_full(wc % kStages), (wc / kStages) & 1u);
+        bool w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full(wc % kStages), (wc / kStages) & 1u));
         bool a_ready = true;
 #pragma unroll
         for (int c = 0; c < kNumChunks; ++c) {
           const MmaChunk op = mma_chunk(c);
           const uint32_t s = wc % kStages;
-          FN_TRACE(tile_cnt == 2, tslot++);
+          FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
           if (op.gated && !a_ready) mbar_wait(bar_act(op.kb), act_cnt & 1u);
           if (!w_ready) mbar_wait(bar_full(s), (wc / kStages) & 1u);
           tc_fence_after();
-          FN_TRACE(tile_cnt == 2, tslot++);
+          FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
           // probe the next chunk's barriers now; the answers are needed only after this chunk is issued
           const uint32_t act_next = act_cnt + ((op.gated && op.kb == 3) ? 1u : 0u);
-          w_ready = mbar_test_wait(bar_full((wc + 1) % kStages), ((wc + 1) / kStages) & 1u);
+          w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full((wc + 1) % kStages), ((wc + 1) / kStages) & 1u));
           if (c + 1 < kNumChunks) {
             const MmaChunk nx = mma_chunk(c + 1);
-            a_ready = nx.gated ? mbar_test_wait(bar_act(nx.kb), act_next & 1u) : true;
+            a_ready = nx.gated ? __all_sync(0xffffffffu, mbar_test_wait(bar_act(nx.kb), act_next & 1u)) : true;
           } else {
             a_ready = true;
           }
-          const uint64_t a_desc = (op.a_sel == 0 ? desc_act + (uint64_t)(op.kb * (kKBlockBytes >> 4)) : desc_pe);
-          const uint64_t b_desc = desc_w + (uint64_t)(s * (kBigChunkBytes >> 4));
+          const uint64_t a_desc = (op.a_sel == 0 ? desc_act + (uint64_t)(op.kb * (kKBlockBytes >> 4))
+                                                 : (op.a_sel == 1 ? desc_pe : desc_ped)) + (uint64_t)(2 * op.kstep0);
+          const uint64_t b_desc = desc_w + (uint64_t)(s * (kBigChunkBytes >> 4)) + (uint64_t)(2 * op.kstep0);
           const uint32_t idesc = op.n128 ? idesc128 : idesc256;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < op.ksteps; ++ks)
-            umma_bf16(acc_addr[op.acc], a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
-                      (op.fresh && ks == 0) ? 0u : 1u);
-          umma_commit(bar_empty(s));
-          if (op.commit_acc) umma_commit(bar_acc(op.acc));
-          FN_TRACE(tile_cnt == 2, tslot++);
+            for (int ks = 0; ks < op.ksteps; ++ks)
+              umma_bf16(acc_addr[op.acc], a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
+                        (op.fresh && ks == 0) ? 0u : 1u);
+            umma_commit(bar_empty(s));
+            if (op.commit_acc) umma_commit(bar_acc(op.acc));
+          }
+          __syncwarp();
+          FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
           act_cnt = act_next;
           ++wc;
         }
@@ -261,9 +258,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     const uint32_t row = q * 32u + (uint32_t)lane;
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     uint32_t acc_cnt[2] = {0u, 0u};
-    uint32_t wtile = 0, wslot = 256 + grp * 64;   // tracer: per group 64 slots from 256 (lane 0 of quadrant-0 warp)
+    [[maybe_unused]] uint32_t wtile = 0, wslot = 256 + grp * 64;   // tracer: 64 slots per group from 256
     const uint32_t act_row = base + kOffAct + row * 128u;
-    uint32_t ped_pk[16];                                    // group 1: packed direction encoding of this row
+    uint8_t* ped_row_ptr = base_ptr + kOffPed + row * 128u;
     for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride) {
       const int64_t g = tile * kTileM + row;
       const int64_t gc = g < P.M ? g : P.M - 1;
@@ -300,6 +297,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         float d[32];
 #pragma unroll
         for (int i = kPED; i < 32; ++i) d[i] = 0.0f;
+        d[kBiasColHi] = 1.0f;               // the two "ones" columns every layer's BIAS chunk multiplies
+        d[kBiasColLo] = 1.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float p = P.viewdirs[3 * ray + c];
@@ -315,8 +314,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
             sn = s2;
           }
         }
+        const uint32_t ped_row = base + kOffPed + row * 128u;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ped_pk[i] = pack_bf16(d[2 * i], d[2 * i + 1]);   // stored after layer 5
+        for (int c16 = 0; c16 < 4; ++c16)
+          st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4),
+                       pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
+                       pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
+        fence_proxy_async_smem();
+        mbar_arrive(bar_pe);
       }
 
       const float* rowbias = nullptr;
@@ -334,14 +339,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         FN_TRACE(wtile == 2 && row == 0, wslot++);
         ++acc_cnt[a];
         tc_fence_after();
-        if (step == 5 && grp == 1) {        // layer 5's MMAs are complete: the xyz tile is dead, reuse it
-          const uint32_t ped_row = base + kOffPed + row * 128u;
-#pragma unroll
-          for (int c16 = 0; c16 < 4; ++c16)
-            st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4), ped_pk[4 * c16], ped_pk[4 * c16 + 1],
-                         ped_pk[4 * c16 + 2], ped_pk[4 * c16 + 3]);
-        }                                   // (made visible by the fence before this thread's next arrive)
-        const float* bias_s = aux_s + (step < 8 ? kAuxBiasPts + step * 256 : kAuxBiasFeat);
         const uint32_t tacc = tmem_row + (uint32_t)a * 256u;
 #pragma unroll 1
         for (int round = 0; round < 2; ++round) {
@@ -350,36 +347,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const uint32_t col0 = unit * 32u;
           const uint32_t dst = act_row + kb * kKBlockBytes;
           if (step == 8)
-            epilogue_unit<false, false, false>(tacc + col0, bias_s + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
+            epilogue_unit<false, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
           else if (step == 7)
-            epilogue_unit<true, true, false>(tacc + col0, bias_s + col0, aux_s + kAuxWAlpha + col0, nullptr, dst, half * 4u, row, sigma);
+            epilogue_unit<true, true, false>(tacc + col0, heads_s + col0, nullptr, dst, half * 4u, row, sigma);
           else if (step == 5 && P.cond)
-            epilogue_unit<true, false, true>(tacc + col0, bias_s + col0, nullptr, rowbias + col0, dst, half * 4u, row, sigma);
+            epilogue_unit<true, false, true>(tacc + col0, nullptr, rowbias + col0, dst, half * 4u, row, sigma);
           else
-            epilogue_unit<true, false, false>(tacc + col0, bias_s + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
-#ifdef FNERF_TRACE
-          long long* tr = (blockIdx.x == 0 && wtile == 2 && row == 0 && g_trace_buf && step == 2) ? g_trace_buf + 512 + grp * 32 + round * 16 : nullptr;
-          if (tr) tr[0] = clock64();
-#endif
-#ifndef EXP_NOFENCE
+            epilogue_unit<true, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
           fence_proxy_async_smem();
-#endif
-#ifdef FNERF_TRACE
-          if (tr) tr[1] = clock64();
-#endif
           tc_fence_before();
-#ifdef FNERF_TRACE
-          if (tr) tr[2] = clock64();
-#endif
-#ifdef EXP_WARP_ARRIVE
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_act(kb));
-#else
           mbar_arrive(bar_act(kb));
-#endif
-#ifdef FNERF_TRACE
-          if (tr) tr[3] = clock64();
-#endif
           FN_TRACE(wtile == 2 && row == 0, wslot++);
         }
       }
@@ -392,28 +369,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         uint32_t v[32];
         tmem_ld32(tmem_row + 256u + grp * 32u, v);
         tmem_ld_wait();
+        const float* wrgb = heads_s + (kAuxWRgb - kAuxWAlpha);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = (int)grp * 32 + j;
-          const float h = fmaxf(__uint_as_float(v[j]) + aux_s[kAuxBiasViews + col], 0.0f);
-          c0 = fmaf(h, aux_s[kAuxWRgb + col], c0);
-          c1 = fmaf(h, aux_s[kAuxWRgb + kWV + col], c1);
-          c2 = fmaf(h, aux_s[kAuxWRgb + 2 * kWV + col], c2);
+          const float h = fmaxf(__uint_as_float(v[j]), 0.0f);         // view-layer bias is in the accumulator
+          c0 = fmaf(h, wrgb[col], c0);
+          c1 = fmaf(h, wrgb[kWV + col], c1);
+          c2 = fmaf(h, wrgb[2 * kWV + col], c2);
         }
         tc_fence_before();
         // partials of groups 1..3 park in the unused upper half (logical chunks 5..7) of this row of
-        // the encoding buffer; the view layer's MMAs (its only async-proxy reader) are complete
-        uint8_t* enc_row = base_ptr + kOffPe + row * 128u;
-        if (grp != 0) *reinterpret_cast<float4*>(enc_row + (((4u + grp) ^ (row & 7u)) << 4)) = make_float4(c0, c1, c2, sigma);
+        // the direction tile; the view layer's MMAs (its last async-proxy readers this tile) are complete
+        if (grp != 0) *reinterpret_cast<float4*>(ped_row_ptr + (((4u + grp) ^ (row & 7u)) << 4)) = make_float4(c0, c1, c2, sigma);
         worker_bar_sync();
         if (grp == 0) {
-          const float4 p1 = *reinterpret_cast<const float4*>(enc_row + ((5u ^ (row & 7u)) << 4));
-          const float4 p2 = *reinterpret_cast<const float4*>(enc_row + ((6u ^ (row & 7u)) << 4));
-          const float4 p3 = *reinterpret_cast<const float4*>(enc_row + ((7u ^ (row & 7u)) << 4));
-          c0 = aux_s[kAuxBRgb] + ((c0 + p1.x) + (p2.x + p3.x));
-          c1 = aux_s[kAuxBRgb + 1] + ((c1 + p1.y) + (p2.y + p3.y));
-          c2 = aux_s[kAuxBRgb + 2] + ((c2 + p1.z) + (p2.z + p3.z));
-          const float sg = aux_s[kAuxBAlpha] + ((sigma + p1.w) + (p2.w + p3.w));
+          const float4 p1 = *reinterpret_cast<const float4*>(ped_row_ptr + ((5u ^ (row & 7u)) << 4));
+          const float4 p2 = *reinterpret_cast<const float4*>(ped_row_ptr + ((6u ^ (row & 7u)) << 4));
+          const float4 p3 = *reinterpret_cast<const float4*>(ped_row_ptr + ((7u ^ (row & 7u)) << 4));
+          const float* brgb = heads_s + (kAuxBRgb - kAuxWAlpha);
+          c0 = brgb[0] + ((c0 + p1.x) + (p2.x + p3.x));
+          c1 = brgb[1] + ((c1 + p1.y) + (p2.y + p3.y));
+          c2 = brgb[2] + ((c2 + p1.z) + (p2.z + p3.z));
+          const float sg = heads_s[kAuxBAlpha - kAuxWAlpha] + ((sigma + p1.w) + (p2.w + p3.w));
           if (g < P.M) P.raw[g] = make_float4(c0, c1, c2, sg);
         }
       }

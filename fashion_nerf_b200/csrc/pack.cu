@@ -5,19 +5,6 @@
 
 namespace fnerf {
 
-struct ChunkSrc { int layer, rows, colbase, valid; };
-__host__ __device__ inline ChunkSrc chunk_src(int c, int cond) {
-  const int hoff = kPE + (cond ? kCond : 0);
-  if (c == 0) return {0, 256, 0, kPE};
-  if (c <= 16) return {1 + (c - 1) / 4, 256, ((c - 1) % 4) * 64, 64};
-  if (c == 17) return {5, 256, 0, kPE};
-  if (c <= 21) return {5, 256, hoff + (c - 18) * 64, 64};
-  if (c <= 29) return {6 + (c - 22) / 4, 256, ((c - 22) % 4) * 64, 64};
-  if (c <= 33) return {9, 256, (c - 30) * 64, 64};
-  if (c <= 37) return {10, 128, (c - 34) * 64, 64};
-  return {10, 128, 256, kPED};
-}
-
 __global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict__ packed, int cond) {
   const int64_t total = (int64_t)kBigChunks * 256 * 64 + (int64_t)kSmallChunks * 128 * 64;
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -26,13 +13,25 @@ __global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict_
   const int64_t big = (int64_t)kBigChunks * 256 * 64;
   if (e < big) { c = (int)(e / (256 * 64)); within = (int)(e % (256 * 64)); }
   else { c = kBigChunks + (int)((e - big) / (128 * 64)); within = (int)((e - big) % (128 * 64)); }
-  const int r = within >> 6, k = within & 63;
-  const ChunkSrc cs = chunk_src(c, cond);
-  const LayerDim d = layer_dim(cs.layer, cond);
+  const int r = within >> 6, k = within & 63;          // output feature r, K column k of the chunk
+  const ChunkDesc cd = chunk_desc(c);
+  const LayerDim d = layer_dim(cd.layer, cond);
+  const float* W = flat + flat_weight_offset(cd.layer, cond);
+  const float* bvec = flat + flat_bias_offset(cd.layer, cond);
   float v = 0.0f;
-  if (k < cs.valid) v = flat[flat_weight_offset(cs.layer, cond) + (int64_t)r * d.in + cs.colbase + k];
-  __nv_bfloat16 b = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(packed + chunk_offset(c) + sw128_offset(r, k)) = b;
+  if (cd.kind == CHUNK_TRUNK) {
+    const int base = (cd.layer == 5) ? kPE + (cond ? kCond : 0) : 0;
+    v = W[(int64_t)r * d.in + base + cd.kb * 64 + k];
+  } else if (cd.kind == CHUNK_XYZ) {
+    if (k < kPE) v = W[(int64_t)r * d.in + k];
+  } else {                                             // BIAS / DIR: bias as bf16 hi + lo
+    if (cd.kind == CHUNK_DIR && k < kPED) v = W[(int64_t)r * d.in + kW + k];
+    const float b = bvec[r];
+    const float hi = __bfloat162float(__float2bfloat16_rn(b));
+    if (k == kBiasColHi) v = hi;
+    if (k == kBiasColLo) v = b - hi;
+  }
+  *reinterpret_cast<__nv_bfloat16*>(packed + chunk_offset(c) + sw128_offset(r, k)) = __float2bfloat16_rn(v);
 }
 
 __global__ void k_pack_aux(const float* __restrict__ flat, float* __restrict__ aux, int cond) {

@@ -51,17 +51,10 @@ if __name__ == "__main__":
         print(os.environ.get("FNERF_TRACE_VARIANT", "base"), "tile span", max(t[:117]) - min(x for x in t[:117] if x),
               "mean unit", sum(units) / len(units), "mean acc wait", sum(waits) / len(waits))
         sys.exit(0)
-    print("unit tail at step 2 (cycles): fence.proxy.async, tcgen05.fence::before, mbarrier.arrive")
-    wg = [t[256 + g_ * 64:256 + g_ * 64 + 64] for g_ in range(4)]
-    for grp in range(4):
-        for rnd in range(2):
-            u = t[512 + grp * 32 + rnd * 16: 512 + grp * 32 + rnd * 16 + 4]
-            acc_ready = wg[grp][4 * 2 + 1]
-            if u[0]:
-                print(f"  grp {grp} round {rnd}: math+sts done at +{u[0]-acc_ready:5d} after acc-ready | fence {u[1]-u[0]:4d} tcfence {u[2]-u[1]:4d} arrive {u[3]-u[2]:4d}")
     print("MMA issuer: per chunk (before weights wait, weights ready, issued) relative cycles")
-    names = ["L0"] + [f"L{l}k{k}" for l in range(1, 5) for k in range(4)] + ["L5pe"] + [f"L5k{k}" for k in range(4)] + \
-            [f"L{l}k{k}" for l in (6, 7) for k in range(4)] + [f"Fk{k}" for k in range(4)] + [f"Vk{k}" for k in range(4)] + ["Vd"]
+    names = ["L0pe", "L0b"] + [f"L{l}{k}" for l in range(1, 5) for k in ("k0", "k1", "k2", "k3", "b")] + ["L5pe"] + \
+            [f"L5{k}" for k in ("k0", "k1", "k2", "k3", "b")] + [f"L{l}{k}" for l in (6, 7) for k in ("k0", "k1", "k2", "k3", "b")] + \
+            [f"F{k}" for k in ("k0", "k1", "k2", "k3", "b")] + [f"V{k}" for k in ("k0", "k1", "k2", "k3", "d")]
     for i, n in enumerate(names):
         a, b, c = t[3 * i:3 * i + 3]
         if a:
