@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 256);   // two worker groups per K-block
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 8);     // one arrive per warp: 2 groups x 4 warps per K-block
     mbar_init(bar_pe, 256);                                       // encoding groups 0 and 1
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
@@ -183,8 +183,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const uint32_t s = wc % kStages;
           mbar_wait(bar_empty(s), ((wc / kStages) & 1u) ^ 1u);
           const uint32_t bytes = (uint32_t)chunk_bytes(c);
+#ifdef EXP_NOTMA
+          mbar_arrive(bar_full(s)); (void)bytes;
+#else
           mbar_expect_tx(bar_full(s), bytes);
           bulk_g2s(base + kOffW + s * kBigChunkBytes, P.packed + chunk_offset(c), bytes, bar_full(s));
+#endif
         }
       }
     }
@@ -239,6 +243,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < op.ksteps; ++ks)
+#ifdef EXP_NOMMA
+              if (P.M < 0)
+#endif
               umma_bf16(acc_addr[op.acc], a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
                         (op.fresh && ks == 0) ? 0u : 1u);
             umma_commit(bar_empty(s));
@@ -354,9 +361,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
             epilogue_unit<true, false, true>(tacc + col0, nullptr, rowbias + col0, dst, half * 4u, row, sigma);
           else
             epilogue_unit<true, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
+          // every lane publishes its own stores to the async proxy; one lane per warp then arrives
+          // (512 per-thread arrives on two barriers cost ~10 % of the epilogue in SYNCS throttling)
           fence_proxy_async_smem();
           tc_fence_before();
-          mbar_arrive(bar_act(kb));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_act(kb));
           FN_TRACE(wtile == 2 && row == 0, wslot++);
         }
       }
