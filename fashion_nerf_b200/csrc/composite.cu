@@ -301,10 +301,115 @@ k_composite_bwd(const float4* __restrict__ raw, const float* __restrict__ z,
   }
 }
 
+// Register-resident backward for S <= 32*NB: raw and z are read ONCE (all loads up front), the forward
+// scan keeps alpha / T / w*v per block in registers, the reverse scan writes g_raw.  Same arithmetic
+// as k_composite_bwd above.
+template <int NB>
+__global__ void __launch_bounds__(kCompWarps * 32)
+k_composite_bwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
+                    const float* __restrict__ dnorm, const float* __restrict__ g_rgb,
+                    const float* __restrict__ g_depth, const float* __restrict__ g_acc,
+                    float4* __restrict__ g_raw, int64_t R, int S, int white) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  const int64_t warp_stride = (int64_t)gridDim.x * kCompWarps;
+  for (int64_t r = warp_global; r < R; r += warp_stride) {
+    const float4* rawr = raw + r * S;
+    const float* zr = z + r * S;
+    float4 rv[NB];
+    float zv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = b * 32 + lane;
+      rv[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      zv[b] = 0.f;
+      if (i < S) { rv[b] = ldg_stream4(rawr + i); zv[b] = ldg_stream(zr + i); }
+    }
+    const float dn = dnorm[r];
+    const float gr = g_rgb[3 * r], gg = g_rgb[3 * r + 1], gb = g_rgb[3 * r + 2];
+    const float gd = g_depth ? g_depth[r] : 0.0f;
+    float ga = g_acc ? g_acc[r] : 0.0f;
+    if (white) ga -= (gr + gg + gb);
+
+    float Tb[NB], alb[NB], distb[NB], vb[NB];
+    float carry = 1.0f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = b * 32 + lane;
+      Tb[b] = 0.f; alb[b] = 0.f; distb[b] = 0.f; vb[b] = 0.f;
+      if (b * 32 < S) {
+        float z_up = __shfl_down_sync(0xffffffffu, zv[b], 1);
+        const float z_first_next = (b + 1 < NB) ? __shfl_sync(0xffffffffu, zv[(b + 1 < NB) ? b + 1 : b], 0) : 0.f;
+        if (lane == 31) z_up = z_first_next;
+        const bool valid = i < S;
+        float dist = (i == S - 1) ? 1e10f : (z_up - zv[b]);
+        dist *= dn;
+        const float alpha = valid ? (1.0f - expf(-fmaxf(rv[b].w, 0.0f) * dist)) : 0.0f;
+        float p = valid ? (1.0f - alpha + 1e-10f) : 1.0f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_up_sync(0xffffffffu, p, o);
+          if (lane >= o) p *= n;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, p, 1);
+        if (lane == 0) excl = 1.0f;
+        Tb[b] = carry * excl;
+        carry *= __shfl_sync(0xffffffffu, p, 31);
+        alb[b] = alpha;
+        distb[b] = dist;
+        // the colour terms are recomputed in the reverse pass; v needs them now
+        vb[b] = valid ? (gr * sigmoidf_(rv[b].x) + gg * sigmoidf_(rv[b].y) + gb * sigmoidf_(rv[b].z) + gd * zv[b] + ga) : 0.0f;
+      }
+    }
+    float tail = 0.0f;
+#pragma unroll
+    for (int b = NB - 1; b >= 0; --b) {
+      const int i = b * 32 + lane;
+      if (b * 32 < S) {
+        const bool valid = i < S;
+        const float wv = valid ? alb[b] * Tb[b] * vb[b] : 0.0f;
+        float q = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_down_sync(0xffffffffu, q, o);
+          if (lane + o < 32) q += n;
+        }
+        const float suffix = (q - wv) + tail;
+        tail += __shfl_sync(0xffffffffu, q, 0);
+        if (valid) {
+          const float om = 1.0f - alb[b] + 1e-10f;
+          const float w = alb[b] * Tb[b];
+          const float cr = sigmoidf_(rv[b].x), cg = sigmoidf_(rv[b].y), cb = sigmoidf_(rv[b].z);
+          const float g_alpha = Tb[b] * vb[b] - suffix / om;
+          const float g_sigma = (rv[b].w > 0.0f) ? distb[b] * (1.0f - alb[b]) * g_alpha : 0.0f;
+          g_raw[r * S + i] = make_float4(w * gr * cr * (1.0f - cr), w * gg * cg * (1.0f - cg),
+                                         w * gb * cb * (1.0f - cb), g_sigma);
+        }
+      }
+    }
+  }
+}
+
 int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* g_rgb,
                          const float* g_depth, const float* g_acc, float* g_raw, int64_t R,
                          int64_t S, int white, cudaStream_t s) {
   if (R == 0) return 0;
+  if (S <= 256) {
+    int64_t nb = (R + kCompWarps - 1) / kCompWarps;
+    const int64_t capr = (int64_t)num_sms() * 8 * 4;
+    if (nb > capr) nb = capr;
+    const unsigned g = (unsigned)nb, t = kCompWarps * 32;
+    const float4* raw4 = (const float4*)raw;
+    float4* g4 = (float4*)g_raw;
+    switch ((S + 31) / 32) {
+      case 1: k_composite_bwd_reg<1><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      case 2: k_composite_bwd_reg<2><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      case 3: case 4: k_composite_bwd_reg<4><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      case 5: case 6: k_composite_bwd_reg<6><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      default: k_composite_bwd_reg<8><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+    }
+    return check_launch("composite_bwd");
+  }
   const size_t smem = (size_t)kBwdWarps * 2 * S * sizeof(float);
   if (smem > 200 * 1024) return set_error(FNERF_ERR_SIZE, "composite_bwd: S too large");
   if (smem > 48 * 1024) {

@@ -254,3 +254,35 @@ def test_error_codes_and_no_cpu_fallback(F, cuda_device):
     assert lib.fnerf_importance(None, None, None, 0, None, None, None, None, 4, 2, 4, None) == -2
     with pytest.raises(F.FnerfError):
         F.ops.ray_setup(torch.zeros(4, 3))                              # CPU tensor: rejected, not emulated
+
+
+def test_importance_descending_coarse_depths(F, cuda_device):
+    """near > far gives descending coarse depths: the rank-merge fast path must hand over to the
+    generic sort, and odd sizes must still be bit-exact."""
+    for R, Nc, Nf in ((257, 64, 128), (33, 20, 45)):
+        g = _gen(31)
+        near, far = torch.full((R,), 6.0), torch.full((R,), 2.0)
+        z = O.stratified(near, far, torch.linspace(0, 1, Nc), torch.rand(R, Nc, generator=g))
+        assert (z[:, 1:] < z[:, :-1]).all()
+        w = torch.rand(R, Nc, generator=g)
+        u = torch.rand(R, Nf, generator=g)
+        ref = O.sample_pdf(z, w, u)
+        got = F.ops.importance(z.to(cuda_device), w.to(cuda_device), u.to(cuda_device))
+        assert torch.equal(got["inds"].cpu().long(), ref["inds"])
+        assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
+        assert torch.equal(got["z_f"].cpu(), ref["z_f"])
+
+
+def test_importance_ties_and_duplicates(F, cuda_device):
+    """Duplicate u values and samples equal to coarse depths: merged output must equal torch.sort's."""
+    R, Nc, Nf = 64, 32, 96
+    g = _gen(32)
+    z = torch.sort(torch.rand(R, Nc, generator=g) * 4 + 2, -1)[0]
+    z[:, 10] = z[:, 9]                                                 # duplicate coarse depths
+    w = torch.rand(R, Nc, generator=g)
+    u = torch.rand(R, Nf, generator=g)
+    u[:, 1::2] = u[:, 0::2]                                            # duplicate uniforms -> duplicate samples
+    ref = O.sample_pdf(z, w, u)
+    got = F.ops.importance(z.to(cuda_device), w.to(cuda_device), u.to(cuda_device))
+    assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
+    assert torch.equal(got["z_f"].cpu(), ref["z_f"])
