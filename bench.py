@@ -39,6 +39,8 @@ NEAR, FAR = 2.0, 6.0
 FLOP_PER_SAMPLE = 1_186_816          # un-padded 593,408 MAC
 FLOP_PER_RAY = FLOP_PER_SAMPLE * (N_C + N_C + N_F)
 CPU_SAMPLE_RAYS = 4096
+WORKLOAD = ("single-B200 full-frame 800x800 render per GPU (BASELINE configs[1]); view r of N per rank, "
+            "random-init 8x256 NeRF MLPs (seeds 0/1), L=10/4 PE")
 
 
 def _peaks():
@@ -139,8 +141,9 @@ def run_reference(args):
         "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "single-B200 full-frame 800x800 render (BASELINE configs[1]); bounded CPU sample",
-                   "rays_per_step": CPU_SAMPLE_RAYS, "N_samples": N_C, "N_importance": N_F},
+        "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": H * W, "N_samples": N_C, "N_importance": N_F,
+                   "reference_sample_rays_per_step": CPU_SAMPLE_RAYS,
+                   "parallelism": "host cores of rank 0 only"},
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -270,9 +273,7 @@ def main():
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision if not use_bf16 else "bf16",
             "data": "synthetic",
-            "config": {"workload": "single-B200 full-frame 800x800 render per GPU (BASELINE configs[1]); "
-                                   "view r of N per rank, random-init 8x256 NeRF MLPs (seeds 0/1), L=10/4 PE",
-                       "rays_per_gpu_per_step": R, "N_samples": N_C, "N_importance": N_F,
+            "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": R, "N_samples": N_C, "N_importance": N_F,
                        "l2_policy": "inputs+intermediates per step (~2.7 GB) exceed the 126 MB L2",
                        "parallelism": f"ray-sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
