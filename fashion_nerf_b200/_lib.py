@@ -8,7 +8,7 @@ import os
 from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfnerf.so")
+LIB_PATH = os.environ.get("FNERF_LIB") or os.path.join(HERE, "libfnerf.so")   # FNERF_LIB: A/B builds (tools/)
 
 ABI_VERSION = 1
 PRECISION_FP32 = 0
