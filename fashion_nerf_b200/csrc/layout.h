@@ -107,6 +107,14 @@ FN_HD int64_t simt_offset_floats(int j, int cond) {
 }
 FN_HD int64_t packed_bytes(int cond) { return kSecCOffset + simt_offset_floats(10, cond) * 4; }
 
+// ---- training tape (bf16 tensor-core backward) ----------------------------------------------------
+// Per 128-sample tile, a sequence of 16 KB K-block images: 128 rows (samples) x 64 bf16 columns with the
+// 128-byte swizzle, i.e. the forward kernel's shared-memory bytes verbatim, so the backward kernels load
+// them with one bulk copy each.  Forward slots: xyz encoding, direction encoding (+ ones in cols 27, 28),
+// H0..H7 (4 K-blocks each), feature (4), view-layer output HV (2).
+constexpr int kTapeSlotPe = 0, kTapeSlotPed = 1, kTapeSlotH = 2, kTapeSlotFeat = 2 + 32, kTapeSlotHv = 2 + 36;
+constexpr int kTapeFwdSlots = 40;
+
 // swizzled byte offset of element (row r, column k in [0,64)) inside a chunk / activation K-block
 FN_HD uint32_t sw128_offset(uint32_t r, uint32_t k) {
   return r * 128u + ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));

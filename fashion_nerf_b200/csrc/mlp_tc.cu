@@ -90,6 +90,7 @@ struct TcParams {
   const float* cond_proj; const int32_t* cond_index; int64_t C;
   float4* raw;
   int64_t M; int S; int64_t ntiles; int cond;
+  uint8_t* tape;   // kSave only: per tile kTapeFwdSlots K-block images (layout.h), the shared-memory bytes verbatim
 };
 
 // epilogue of one 32-column unit: TMEM -> (+rowbias) -> [ReLU] -> bf16 -> swizzled smem.  The layer
@@ -98,7 +99,8 @@ struct TcParams {
 template <bool kRelu, bool kSigma, bool kCond>
 __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __restrict__ walpha_s,
                                               const float* __restrict__ rowbias, uint32_t act_row_addr,
-                                              uint32_t chunk0, uint32_t row, float& sigma) {
+                                              uint32_t chunk0, uint32_t row, float& sigma,
+                                              uint8_t* __restrict__ save_row = nullptr) {
   uint32_t v[32];
   tmem_ld32(taddr, v);
   tmem_ld_wait();
@@ -132,11 +134,14 @@ __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __res
     }
     const uint32_t c16 = chunk0 + (uint32_t)c;
     st_shared_v4(act_row_addr + ((c16 ^ (row & 7u)) << 4), p0, p1, p2, p3);
+    if (save_row != nullptr)   // training tape: the same 16 bytes at the same swizzled offset of the K-block image
+      *reinterpret_cast<uint4*>(save_row + ((c16 ^ (row & 7u)) << 4)) = make_uint4(p0, p1, p2, p3);
   }
 }
 
 __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
 
+template <bool kSave>
 __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -272,6 +277,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
       const int64_t g = tile * kTileM + row;
       const int64_t gc = g < P.M ? g : P.M - 1;
       const int64_t ray = gc / P.S;
+      uint8_t* tape_row = kSave ? P.tape + (size_t)tile * kTapeFwdSlots * kKBlockBytes + row * 128u : nullptr;
       // ---- positional encodings (A.3): sincos once, then double-angle recurrence per octave -----
       if (grp == 0) {
         const float zv = P.z[gc];
@@ -294,10 +300,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         }
         const uint32_t pe_row = base + kOffPe + row * 128u;
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16)
-          st_shared_v4(pe_row + (((uint32_t)c16 ^ (row & 7u)) << 4),
-                       pack_bf16(f[c16 * 8 + 0], f[c16 * 8 + 1]), pack_bf16(f[c16 * 8 + 2], f[c16 * 8 + 3]),
-                       pack_bf16(f[c16 * 8 + 4], f[c16 * 8 + 5]), pack_bf16(f[c16 * 8 + 6], f[c16 * 8 + 7]));
+        for (int c16 = 0; c16 < 8; ++c16) {
+          const uint4 pk = make_uint4(pack_bf16(f[c16 * 8 + 0], f[c16 * 8 + 1]), pack_bf16(f[c16 * 8 + 2], f[c16 * 8 + 3]),
+                                      pack_bf16(f[c16 * 8 + 4], f[c16 * 8 + 5]), pack_bf16(f[c16 * 8 + 6], f[c16 * 8 + 7]));
+          st_shared_v4(pe_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
+          if (kSave) *reinterpret_cast<uint4*>(tape_row + kTapeSlotPe * kKBlockBytes + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
+        }
         fence_proxy_async_smem();
         mbar_arrive(bar_pe);
       } else if (grp == 1) {
@@ -323,10 +331,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         }
         const uint32_t ped_row = base + kOffPed + row * 128u;
 #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16)
-          st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4),
-                       pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
-                       pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
+        for (int c16 = 0; c16 < 8; ++c16) {
+          uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+          if (c16 < 4) {
+            pk = make_uint4(pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
+                            pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
+            st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
+          }
+          // the saved image is complete (zeros in columns 32..63): wgrad multiplies all 64 columns
+          if (kSave) *reinterpret_cast<uint4*>(tape_row + kTapeSlotPed * kKBlockBytes + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
+        }
         fence_proxy_async_smem();
         mbar_arrive(bar_pe);
       }
@@ -353,14 +367,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const uint32_t kb = unit >> 1, half = unit & 1u;
           const uint32_t col0 = unit * 32u;
           const uint32_t dst = act_row + kb * kKBlockBytes;
+          uint8_t* sv = kSave ? tape_row + (size_t)(kTapeSlotH + 4 * step + (int)kb) * kKBlockBytes : nullptr;   // H0..H7, FEAT
           if (step == 8)
-            epilogue_unit<false, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
+            epilogue_unit<false, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma, sv);
           else if (step == 7)
-            epilogue_unit<true, true, false>(tacc + col0, heads_s + col0, nullptr, dst, half * 4u, row, sigma);
+            epilogue_unit<true, true, false>(tacc + col0, heads_s + col0, nullptr, dst, half * 4u, row, sigma, sv);
           else if (step == 5 && P.cond)
-            epilogue_unit<true, false, true>(tacc + col0, nullptr, rowbias + col0, dst, half * 4u, row, sigma);
+            epilogue_unit<true, false, true>(tacc + col0, nullptr, rowbias + col0, dst, half * 4u, row, sigma, sv);
           else
-            epilogue_unit<true, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma);
+            epilogue_unit<true, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma, sv);
           // every lane publishes its own stores to the async proxy; one lane per warp then arrives
           // (512 per-thread arrives on two barriers cost ~10 % of the epilogue in SYNCS throttling)
           fence_proxy_async_smem();
@@ -387,6 +402,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           c0 = fmaf(h, wrgb[col], c0);
           c1 = fmaf(h, wrgb[kWV + col], c1);
           c2 = fmaf(h, wrgb[2 * kWV + col], c2);
+        }
+        if (kSave) {             // HV image: 2 K-blocks of 64 columns; this group's 32 columns = 4 chunks
+          uint8_t* hv_row = tape_row + (size_t)(kTapeSlotHv + (int)(grp >> 1)) * kKBlockBytes;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 pk = make_uint4(pack_bf16_relu(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])),
+                                        pack_bf16_relu(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])),
+                                        pack_bf16_relu(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])),
+                                        pack_bf16_relu(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])));
+            const uint32_t c16 = (grp & 1u) * 4u + (uint32_t)c;
+            *reinterpret_cast<uint4*>(hv_row + ((c16 ^ (row & 7u)) << 4)) = pk;
+          }
         }
         tc_fence_before();
         // partials of groups 1..3 park in the unused upper half (logical chunks 5..7) of this row of
@@ -424,16 +451,20 @@ extern "C" int fnerf_debug_set_trace(long long* buf) {
 }
 #endif
 
-int launch_mlp_tc(const MlpArgs& a, cudaStream_t s) {
+// tape == nullptr: render path.  tape != nullptr: training forward, every intermediate activation is also
+// written to the tape as K-block images (mlp_bwd_tc.cu consumes them).
+int launch_mlp_tc_save(const MlpArgs& a, uint8_t* tape, cudaStream_t s) {
   const int64_t M = a.R * a.S;
   if (M == 0) return 0;
-  static bool attr_done[64] = {false};
+  static bool attr_done[64][2] = {{false}};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+  const int sv = tape != nullptr ? 1 : 0;
+  if (dev >= 0 && dev < 64 && !attr_done[dev][sv]) {
+    cudaError_t e = sv ? cudaFuncSetAttribute(k_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)
+                       : cudaFuncSetAttribute(k_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     if (e != cudaSuccess) return set_error((int)e, "mlp_tc attr: %s", cudaGetErrorString(e));
-    attr_done[dev] = true;
+    attr_done[dev][sv] = true;
   }
   TcParams P;
   P.packed = reinterpret_cast<const uint8_t*>(a.packed);
@@ -441,10 +472,14 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t s) {
   P.cond_proj = a.cond_proj; P.cond_index = a.cond_index; P.C = a.C;
   P.raw = reinterpret_cast<float4*>(a.raw);
   P.M = M; P.S = (int)a.S; P.ntiles = (M + kTileM - 1) / kTileM; P.cond = a.cond;
+  P.tape = tape;
   int64_t blocks = num_sms();
   if (blocks > P.ntiles) blocks = P.ntiles;
-  k_mlp_tc<<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
+  if (sv) k_mlp_tc<true><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
+  else k_mlp_tc<false><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
   return check_launch("mlp_tc");
 }
+
+int launch_mlp_tc(const MlpArgs& a, cudaStream_t s) { return launch_mlp_tc_save(a, nullptr, s); }
 
 }  // namespace fnerf
