@@ -135,7 +135,10 @@ int fnerf_mlp_fwd(int precision, const void* packed, int cond, const float* rays
                                            : launch_mlp_fp32(a, (cudaStream_t)stream);
 }
 
-int64_t fnerf_mlp_bwd_workspace_bytes(int64_t R, int64_t S) { return mlp_bwd_workspace_bytes(R, S); }
+int64_t fnerf_mlp_bwd_workspace_bytes(int64_t R, int64_t S) {
+  const int64_t a = mlp_bwd_workspace_bytes(R, S), b = mlp_bwd_tc_workspace_bytes(R * S);   // fp32 chain / bf16 tape
+  return a > b ? a : b;
+}
 
 int fnerf_mlp_bwd(int precision, const void* packed, int cond, const float* rays_o, const float* rays_d,
                   const float* viewdirs, const float* z, const float* cond_proj, const int32_t* cond_index,
@@ -144,8 +147,13 @@ int fnerf_mlp_bwd(int precision, const void* packed, int cond, const float* rays
   int rc = validate_mlp("mlp_bwd", precision, packed, cond, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, g_raw, R, S);
   if (rc != 0 || R == 0) return rc;
   FN_REQUIRE(flat_grad && workspace, FNERF_ERR_NULL, "mlp_bwd: null pointer");
-  FN_REQUIRE(workspace_bytes >= mlp_bwd_workspace_bytes(R, S), FNERF_ERR_WORKSPACE, "mlp_bwd: workspace too small");
+  FN_REQUIRE(workspace_bytes >= fnerf_mlp_bwd_workspace_bytes(R, S), FNERF_ERR_WORKSPACE, "mlp_bwd: workspace too small");
+  FN_REQUIRE(FN_ALIGNED16(workspace) && FN_ALIGNED16(g_raw), FNERF_ERR_ALIGN, "mlp_bwd: workspace / g_raw must be 16-byte aligned");
   MlpArgs a{packed, cond ? 1 : 0, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, nullptr, R, S};
+  // bf16: forward with tape + tcgen05 dgrad chain + tcgen05 wgrad (unconditioned networks); the conditioned
+  // variant and FNERF_PRECISION_FP32 take the fp32 SGEMM chain
+  if (precision == FNERF_PRECISION_BF16 && !cond)
+    return launch_mlp_bwd_tc(a, g_raw, flat_grad, workspace, workspace_bytes, (cudaStream_t)stream);
   return launch_mlp_bwd_fp32(a, g_raw, flat_grad, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -64,6 +64,8 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t s);
 int launch_mlp_tc_save(const MlpArgs& a, uint8_t* tape, cudaStream_t s);   // training forward: also writes the tape
 
 int64_t mlp_bwd_workspace_bytes(int64_t R, int64_t S);
+int64_t mlp_bwd_tc_workspace_bytes(int64_t M);
+int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws, int64_t ws_bytes, cudaStream_t s);
 int launch_mlp_bwd_fp32(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws,
                         int64_t ws_bytes, cudaStream_t s);
 

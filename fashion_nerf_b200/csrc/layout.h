@@ -105,7 +105,20 @@ FN_HD int64_t simt_offset_floats(int j, int cond) {
   for (int i = 0; i < j; ++i) { LayerDim d = layer_dim(simt_layer_id(i), cond); off += (int64_t)d.out * d.in; }
   return off;
 }
-FN_HD int64_t packed_bytes(int cond) { return kSecCOffset + simt_offset_floats(10, cond) * 4; }
+// Section E: TRANSPOSED bf16 chunk stream for the tensor-core dgrad chain (mlp_dgrad_tc.cu), consumption
+// order: view layer (K-blocks 0,1 of its 128 outputs), feature layer (0..3), layers 7..1 (0..3 each).
+// Chunk (layer l, kb) is 256 x 64, K-major, 128-byte swizzle: row k = INPUT feature (trunk block of
+// layer 5: W5[:, hoff + k]), column j = OUTPUT feature 64*kb + j.
+constexpr int kNumChunksT = 34;
+constexpr int kChunkTBytes = 256 * 64 * 2;
+FN_HD int64_t sec_e_offset(int cond) { return (kSecCOffset + simt_offset_floats(10, cond) * 4 + 1023) / 1024 * 1024; }
+struct ChunkTDesc { int layer; int kb; };
+FN_HD ChunkTDesc chunk_t_desc(int c) {
+  if (c < 2) return {10, c};
+  if (c < 6) return {9, c - 2};
+  return {7 - (c - 6) / 4, (c - 6) % 4};
+}
+FN_HD int64_t packed_bytes(int cond) { return sec_e_offset(cond) + (int64_t)kNumChunksT * kChunkTBytes; }
 
 // ---- training tape (bf16 tensor-core backward) ----------------------------------------------------
 // Per 128-sample tile, a sequence of 16 KB K-block images: 128 rows (samples) x 64 bf16 columns with the
@@ -114,6 +127,9 @@ FN_HD int64_t packed_bytes(int cond) { return kSecCOffset + simt_offset_floats(1
 // H0..H7 (4 K-blocks each), feature (4), view-layer output HV (2).
 constexpr int kTapeSlotPe = 0, kTapeSlotPed = 1, kTapeSlotH = 2, kTapeSlotFeat = 2 + 32, kTapeSlotHv = 2 + 36;
 constexpr int kTapeFwdSlots = 40;
+// Backward slots (written by the dgrad chain): dZv (2), dFEAT (4), dZ7 .. dZ0 (4 each).
+constexpr int kTapeBwdSlotZv = 0, kTapeBwdSlotFeat = 2, kTapeBwdSlotZ = 6;   // dZ_l at kTapeBwdSlotZ + 4*(7-l)
+constexpr int kTapeBwdSlots = 38;
 
 // swizzled byte offset of element (row r, column k in [0,64)) inside a chunk / activation K-block
 FN_HD uint32_t sw128_offset(uint32_t r, uint32_t k) {

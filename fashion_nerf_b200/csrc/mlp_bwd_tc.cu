@@ -156,6 +156,135 @@ int launch_wgrad_tc(const WgradParams& P, cudaStream_t s) {
   return check_launch("wgrad_tc");
 }
 
+// ---- bias and head gradients straight from the tape ---------------------------------------------------
+// One CTA per tile, 256 threads = columns.  Reads every dZ image once (HBM-bound) and adds the column
+// sums into the bias gradients; the two tiny heads (sigma: 256->1 on H7, rgb: 128->3 on HV) are fp32 dot
+// products against g_raw.
+__device__ __forceinline__ float tape_elem(const uint8_t* img, int r, int col) {   // image of 128 x 64, column col < 64
+  const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)col & 7u) * 2u;
+  const unsigned short b = *reinterpret_cast<const unsigned short*>(img + off);
+  return __uint_as_float((uint32_t)b << 16);
+}
+
+__global__ void __launch_bounds__(256) k_bias_heads_from_tape(const uint8_t* __restrict__ fwd_tape, const uint8_t* __restrict__ bwd_tape,
+                                                              const float4* __restrict__ g_raw, float* __restrict__ flat_grad,
+                                                              int cond, int64_t M, int64_t ntiles) {
+  __shared__ float4 s_g[128];
+  const int n = threadIdx.x;
+  float bsum[10];                                     // dZ0..dZ7, dFEAT, dZv
+#pragma unroll
+  for (int i = 0; i < 10; ++i) bsum[i] = 0.0f;
+  float wa = 0.0f, wr0 = 0.0f, wr1 = 0.0f, wr2 = 0.0f, gs = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();
+    if (n < 128) {
+      const int64_t g = tile * 128 + n;
+      s_g[n] = g < M ? g_raw[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const uint8_t* ft = fwd_tape + (size_t)tile * kTapeFwdSlots * 16384;
+    const uint8_t* bt = bwd_tape + (size_t)tile * kTapeBwdSlots * 16384;
+    const int kb = n >> 6, col = n & 63;
+#pragma unroll 1
+    for (int l = 0; l < 8; ++l) {
+      const uint8_t* img = bt + (size_t)(kTapeBwdSlotZ + 4 * (7 - l) + kb) * 16384;
+      float a = 0.0f;
+      for (int r = 0; r < 128; ++r) a += tape_elem(img, r, col);
+      bsum[l] += a;
+    }
+    {
+      const uint8_t* img = bt + (size_t)(kTapeBwdSlotFeat + kb) * 16384;
+      const uint8_t* h7 = ft + (size_t)(kTapeSlotH + 28 + kb) * 16384;
+      float a = 0.0f, w = 0.0f;
+      for (int r = 0; r < 128; ++r) { a += tape_elem(img, r, col); w = fmaf(s_g[r].w, tape_elem(h7, r, col), w); }
+      bsum[8] += a; wa += w;
+    }
+    if (n < 128) {
+      const uint8_t* img = bt + (size_t)(kTapeBwdSlotZv + kb) * 16384;
+      const uint8_t* hv = ft + (size_t)(kTapeSlotHv + kb) * 16384;
+      float a = 0.0f;
+      for (int r = 0; r < 128; ++r) {
+        a += tape_elem(img, r, col);
+        const float h = tape_elem(hv, r, col);
+        const float4 gq = s_g[r];
+        wr0 = fmaf(gq.x, h, wr0); wr1 = fmaf(gq.y, h, wr1); wr2 = fmaf(gq.z, h, wr2);
+      }
+      bsum[9] += a;
+    }
+    if (n == 0) for (int r = 0; r < 128; ++r) { gs += s_g[r].w; g0 += s_g[r].x; g1 += s_g[r].y; g2 += s_g[r].z; }
+  }
+  for (int l = 0; l < 8; ++l) atomicAdd(flat_grad + flat_bias_offset(l, cond) + n, bsum[l]);
+  atomicAdd(flat_grad + flat_bias_offset(9, cond) + n, bsum[8]);
+  atomicAdd(flat_grad + flat_weight_offset(8, cond) + n, wa);
+  if (n < 128) {
+    atomicAdd(flat_grad + flat_bias_offset(10, cond) + n, bsum[9]);
+    atomicAdd(flat_grad + flat_weight_offset(11, cond) + n, wr0);
+    atomicAdd(flat_grad + flat_weight_offset(11, cond) + kWV + n, wr1);
+    atomicAdd(flat_grad + flat_weight_offset(11, cond) + 2 * kWV + n, wr2);
+  }
+  if (n == 0) {
+    atomicAdd(flat_grad + flat_bias_offset(8, cond), gs);
+    atomicAdd(flat_grad + flat_bias_offset(11, cond), g0);
+    atomicAdd(flat_grad + flat_bias_offset(11, cond) + 1, g1);
+    atomicAdd(flat_grad + flat_bias_offset(11, cond) + 2, g2);
+  }
+}
+
+int launch_mlp_dgrad_tc(const void* packed, int cond, const float* g_raw, const uint8_t* fwd_tape, uint8_t* bwd_tape,
+                        int64_t M, cudaStream_t s);
+
+int64_t mlp_bwd_tc_workspace_bytes(int64_t M) {
+  const int64_t ntiles = (M + 127) / 128;
+  return ntiles * (int64_t)(kTapeFwdSlots + kTapeBwdSlots) * 16384 + ntiles * 128 * 16 + 4096;
+}
+
+// Full bf16 tensor-core backward of one network query: forward with tape, dgrad chain, wgrad GEMMs, bias /
+// head reductions.  flat_grad += dL/dparams.  (Unconditioned networks; the conditioned variant uses the
+// fp32 path.)
+int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  const int64_t M = a.R * a.S;
+  if (M == 0) return 0;
+  const int64_t ntiles = (M + 127) / 128;
+  if (ws_bytes < mlp_bwd_tc_workspace_bytes(M)) return set_error(FNERF_ERR_WORKSPACE, "mlp_bwd_tc: workspace too small");
+  uint8_t* fwd_tape = reinterpret_cast<uint8_t*>(ws);
+  uint8_t* bwd_tape = fwd_tape + ntiles * (int64_t)kTapeFwdSlots * 16384;
+  float* raw_scratch = reinterpret_cast<float*>(bwd_tape + ntiles * (int64_t)kTapeBwdSlots * 16384);
+  const int cond = 0;
+  MlpArgs fa = a;
+  fa.raw = raw_scratch;
+  int rc;
+  if ((rc = launch_mlp_tc_save(fa, fwd_tape, s))) return rc;
+  if ((rc = launch_mlp_dgrad_tc(a.packed, cond, g_raw, fwd_tape, bwd_tape, M, s))) return rc;
+
+  const int64_t fstride = (int64_t)kTapeFwdSlots * 16384, bstride = (int64_t)kTapeBwdSlots * 16384;
+  auto wg = [&](int dz_slot, int n_kb, int x_slot, int x_kb, float* dw, int64_t ld, int n_valid) {
+    WgradParams P;
+    P.dz = bwd_tape; P.dz_tile_stride = bstride; P.dz_slot0 = dz_slot; P.n_kb = n_kb;
+    P.x = fwd_tape; P.x_tile_stride = fstride; P.x_slot0 = x_slot; P.x_kb = x_kb;
+    P.dw = dw; P.ld = ld; P.n_valid = n_valid; P.ntiles = ntiles;
+    return launch_wgrad_tc(P, s);
+  };
+  auto gw = [&](int l) { return flat_grad + flat_weight_offset(l, cond); };
+  auto zslot = [&](int l) { return kTapeBwdSlotZ + 4 * (7 - l); };
+  const int in5 = kPE + kW;
+  if ((rc = wg(zslot(0), 4, kTapeSlotPe, 1, gw(0), kPE, kPE))) return rc;
+  for (int l = 1; l <= 7; ++l) {
+    if (l == 5) {
+      if ((rc = wg(zslot(5), 4, kTapeSlotPe, 1, gw(5), in5, kPE))) return rc;
+      if ((rc = wg(zslot(5), 4, kTapeSlotH + 4 * 4, 4, gw(5) + kPE, in5, kW))) return rc;
+    } else {
+      if ((rc = wg(zslot(l), 4, kTapeSlotH + 4 * (l - 1), 4, gw(l), kW, kW))) return rc;
+    }
+  }
+  if ((rc = wg(kTapeBwdSlotFeat, 4, kTapeSlotH + 28, 4, gw(9), kW, kW))) return rc;
+  if ((rc = wg(kTapeBwdSlotZv, 2, kTapeSlotFeat, 4, gw(10), kW + kPED, kW))) return rc;
+  if ((rc = wg(kTapeBwdSlotZv, 2, kTapeSlotPed, 1, gw(10) + kW, kW + kPED, kPED))) return rc;
+  int64_t blocks = ntiles < 4 * (int64_t)num_sms() ? ntiles : 4 * (int64_t)num_sms();
+  k_bias_heads_from_tape<<<(unsigned)blocks, 256, 0, s>>>(fwd_tape, bwd_tape, reinterpret_cast<const float4*>(g_raw), flat_grad,
+                                                         cond, M, ntiles);
+  return check_launch("mlp_bwd_tc");
+}
+
 }  // namespace fnerf
 
 // ---- debug entry (tests only): dw[n_kb*64, ld] += dZ^T X from two image buffers ---------------------

@@ -34,6 +34,21 @@ __global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict_
   *reinterpret_cast<__nv_bfloat16*>(packed + chunk_offset(c) + sw128_offset(r, k)) = __float2bfloat16_rn(v);
 }
 
+// Section E: transposed chunks for dgrad: chunk row k = input feature, column j = output feature 64*kb + j
+__global__ void k_pack_bf16_T(const float* __restrict__ flat, uint8_t* __restrict__ secE, int cond) {
+  const int c = blockIdx.x;
+  const ChunkTDesc cd = chunk_t_desc(c);
+  const LayerDim d = layer_dim(cd.layer, cond);
+  const float* W = flat + flat_weight_offset(cd.layer, cond);
+  const int base = (cd.layer == 5) ? kPE + (cond ? kCond : 0) : 0;
+  for (int e = threadIdx.x; e < 256 * 64; e += blockDim.x) {
+    const int k = e >> 6, j = e & 63;
+    const int n = cd.kb * 64 + j;
+    const float v = W[(int64_t)n * d.in + base + k];
+    *reinterpret_cast<__nv_bfloat16*>(secE + (size_t)c * kChunkTBytes + sw128_offset((uint32_t)k, (uint32_t)j)) = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void k_pack_aux(const float* __restrict__ flat, float* __restrict__ aux, int cond) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kAuxFloats) return;
@@ -98,6 +113,7 @@ int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s) {
     const int64_t n = (int64_t)d.out * d.in;
     k_pack_simt<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecCOffset), cond, j);
   }
+  k_pack_bf16_T<<<kNumChunksT, 256, 0, s>>>(flat, p + sec_e_offset(cond), cond);
   return check_launch("pack_weights");
 }
 

@@ -131,7 +131,9 @@ def _backward(ctx, grads):
             gr = zeros3
         g_raw = ops.composite_bwd(raw, z, dnorm, gr.contiguous(), gd, ga, white_bkgd=ctx.white_bkgd)
         flat_grad = torch.zeros(n_params, dtype=torch.float32, device=dev)
-        ops.mlp_bwd(packed, rays_o, rays_d, viewdirs, z, g_raw, flat_grad, cond_rows=cond_rows, cond_index=cidx)
+        # same arithmetic as the forward that produced `raw` (bf16: ReLU masks come from the bf16 forward)
+        ops.mlp_bwd(packed, rays_o, rays_d, viewdirs, z, g_raw, flat_grad, precision=_PRECISION_NAMES[ctx.precision],
+                    cond_rows=cond_rows, cond_index=cidx)
         return flat_grad
 
     if ctx.n_importance > 0:
@@ -145,6 +147,7 @@ def _backward(ctx, grads):
 
 render_rays_op.register_autograd(_backward, setup_context=_setup_context)
 
+_PRECISION_NAMES = {v: k for k, v in ops.PRECISIONS.items()}
 _OUT_NAMES = ["rgb", "disp", "acc", "depth", "rgb0", "disp0", "acc0", "z_std", "z_c", "z_f", "raw_c", "raw_f"]
 
 

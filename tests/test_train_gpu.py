@@ -133,3 +133,127 @@ def test_trainer_step_matches_oracle_adam(F, cuda_device):
     # parameters tightly
     assert (model.coarse.flat.cpu() - ref_c).abs().max() <= 2.5e-4
     assert losses[1][0] < losses[0][0]                                # the step reduces the loss
+
+
+def _bf16_case(seed, R, S, dev):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.rand(R, 3, generator=g) * 2 - 1
+    d = torch.randn(R, 3, generator=g)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0]
+    g_raw = torch.randn(R, S, 4, generator=g)
+    return o, d, z, g_raw
+
+
+@pytest.mark.parametrize("R,S", [(40, 24), (5, 25), (333, 7)])
+def test_mlp_bwd_bf16_matches_bf16_autograd(F, cuda_device, R, S):
+    """Tensor-core backward (tape forward + tcgen05 dgrad + tcgen05 wgrad) vs autograd through the oracle MLP
+    evaluated with the same bf16 rounding points, so both sides see the same ReLU masks up to
+    accumulation-order flips.  Tolerance: 0.12 relative per tensor: on a random-init network a ReLU mask that
+    flips costs 100 % of that element, and rounding-boundary differences between the two forwards cascade
+    into ~1e-4..1e-3 of the masks (measured 2.5e-2 .. 5.1e-2); the flip-free test below pins the arithmetic to
+    1e-2.  Against the pure fp32 oracle the same gradients differ by 4-12 % because ~0.1 % of the masks flip
+    under bf16 forward rounding (checked loosely here)."""
+    dev = cuda_device
+    o, d, z, g_raw = _bf16_case(31, R, S, dev)
+    vd, _ = O.ray_setup(d)
+    p = O.init_params(4, cond=False)
+    pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
+    refs = {}
+    for bf16 in (True, False):
+        pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        raw = O.run_network(pr, pts, vd, None, bf16=bf16)
+        (raw * g_raw).sum().backward()
+        refs[bf16] = {k: v.grad for k, v in pr.items()}
+    net = F.NerfNetwork.from_state_dict(p, dev, cond=False)
+    flat_grad = torch.zeros(net.flat.numel(), device=dev)
+    args = (net.packed, o.to(dev), d.to(dev), vd.to(dev), z.to(dev), g_raw.to(dev), flat_grad)
+    F.ops.mlp_bwd(*args, precision="bf16")
+    got = F.unflatten(flat_grad.cpu(), False)
+    assert torch.isfinite(flat_grad).all()
+    worst = {}
+    for k in refs[True]:
+        worst[k] = _rel_err(got[k], refs[True][k])
+        assert worst[k] <= 0.12, (k, worst[k])
+        assert _rel_err(got[k], refs[False][k]) <= 0.25, k
+    # accumulation semantics
+    F.ops.mlp_bwd(*args, precision="bf16")
+    assert _rel_err(flat_grad.cpu(), 2 * F.flatten_state_dict(got, False)) <= 1e-5
+
+
+def test_mlp_bwd_bf16_multi_tile_linearity(F, cuda_device):
+    """Many tiles per CTA + a ragged tail tile: one call == sum of two half calls (different tile boundaries)."""
+    dev = cuda_device
+    R, S = 1201, 67                                                  # 80467 samples = 628 tiles + 83
+    o, d, z, g_raw = (t.to(dev) for t in _bf16_case(32, R, S, dev))
+    net = F.NerfNetwork.random(4, dev)
+    vd, _ = F.ops.ray_setup(d)
+    full = torch.zeros(net.flat.numel(), device=dev)
+    F.ops.mlp_bwd(net.packed, o, d, vd, z, g_raw, full, precision="bf16")
+    halves = torch.zeros_like(full)
+    for sl in (slice(0, 600), slice(600, R)):
+        F.ops.mlp_bwd(net.packed, o[sl], d[sl], vd[sl], z[sl], g_raw[sl], halves, precision="bf16")
+    assert torch.isfinite(full).all()
+    assert _rel_err(full, halves) <= 1e-4
+    ref = torch.zeros_like(full)
+    F.ops.mlp_bwd(net.packed, o, d, vd, z, g_raw, ref, precision="fp32")
+    sf, sr = F.unflatten(full, False), F.unflatten(ref, False)
+    for k in sr:
+        assert _rel_err(sf[k], sr[k]) <= 0.25, k
+
+
+def test_mlp_bwd_bf16_flip_free(F, cuda_device):
+    """Same comparison on a network whose ReLU masks cannot flip: weights scaled by 0.1 and biases set to +-1
+    per unit, so every unit is >= 10 sigma from zero (always on or always dead).  What is left is bf16
+    rounding of dZ and of the activations: <= 1e-2 relative per tensor; dead units must get exactly zero
+    bias gradient."""
+    dev = cuda_device
+    R, S = 50, 31
+    o, d, z, g_raw = _bf16_case(33, R, S, dev)
+    vd, _ = O.ray_setup(d)
+    p = O.init_params(5, cond=False)
+    g = torch.Generator().manual_seed(34)
+    for k in p:
+        if k.endswith("weight") and not k.startswith(("alpha", "rgb")):
+            p[k] = 0.1 * p[k]
+        if k.endswith("bias") and k.startswith(("pts", "views")):
+            p[k] = (torch.randint(0, 2, p[k].shape, generator=g) * 2 - 1).float()
+    pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    raw = O.run_network(pr, pts, vd, None, bf16=True)
+    (raw * g_raw).sum().backward()
+    net = F.NerfNetwork.from_state_dict(p, dev, cond=False)
+    flat_grad = torch.zeros(net.flat.numel(), device=dev)
+    F.ops.mlp_bwd(net.packed, o.to(dev), d.to(dev), vd.to(dev), z.to(dev), g_raw.to(dev), flat_grad, precision="bf16")
+    got = F.unflatten(flat_grad.cpu(), False)
+    errs = {k: _rel_err(got[k], pr[k].grad) for k in pr}
+    print(errs)
+    for k, e in errs.items():
+        assert e <= 1e-2, (k, e)
+    for k in pr:
+        if k.endswith("bias") and k.startswith(("pts", "views")):
+            dead = p[k] < 0
+            assert (got[k][dead] == 0).all(), k
+
+
+def test_trainer_bf16_tracks_fp32(F, cuda_device):
+    """bf16 forward + bf16 tensor-core backward: the loss trajectory of 6 Adam steps stays within 2e-3 of the
+    all-fp32 trajectory from the same initial parameters, and decreases."""
+    from fashion_nerf_b200.train import Trainer
+    dev = cuda_device
+    o, d = (t.to(dev) for t in O.pinhole_rays(24, 24))
+    R, Nc, Nf = o.shape[0], 32, 48
+    g = torch.Generator().manual_seed(3)
+    u_s, u_f = torch.rand(R, Nc, generator=g).to(dev), torch.rand(R, Nf, generator=g).to(dev)
+    tgt = torch.rand(R, 3, generator=g).to(dev)
+    traj = {}
+    for prec in ("fp32", "bf16"):
+        pc, pf = O.init_params(0), O.init_params(1)
+        for p in (pc, pf):
+            p["alpha_linear.bias"] += 0.1
+        model = F.NerfModel(F.NerfNetwork.from_state_dict(pc, dev), F.NerfNetwork.from_state_dict(pf, dev))
+        tr = Trainer(model)
+        traj[prec] = [tr.step(o, d, tgt, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f, precision=prec)["loss"].item()
+                      for _ in range(6)]
+    assert traj["bf16"][-1] < traj["bf16"][0]
+    for a, b in zip(traj["bf16"], traj["fp32"]):
+        assert abs(a - b) <= 2e-3, traj

@@ -58,7 +58,7 @@ if rank == 0:
     flop = 4096 * 893_190_144            # train fwd+bwd FLOP/ray
     print(json.dumps({"bench": "train_step", "n_gpus": world, "rays_per_gpu": 4096, "ms_per_step": ms,
                       "Mrays_per_s": world * 4096 / ms / 1e3, "algorithmic_TFLOPs_per_gpu": flop / ms / 1e9,
-                      "precision_fwd": args.precision, "bwd": "fp32 SIMT", "loss_first_last": [losses[0], losses[-1]],
+                      "precision_fwd": args.precision, "bwd": "bf16 tcgen05 (tape + dgrad + wgrad)" if args.precision == "bf16" else "fp32 SGEMM chain", "loss_first_last": [losses[0], losses[-1]],
                       "replicas_identical": same}))
 if world > 1:
     dist.barrier()
