@@ -61,7 +61,7 @@ struct MlpArgs {
 };
 int launch_mlp_fp32(const MlpArgs& a, cudaStream_t s);
 int launch_mlp_tc(const MlpArgs& a, cudaStream_t s);
-int launch_mlp_tc_save(const MlpArgs& a, uint8_t* tape, cudaStream_t s);   // training forward: also writes the tape
+int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cudaStream_t s);   // training forward: also writes the tape
 
 int64_t mlp_bwd_workspace_bytes(int64_t R, int64_t S);
 int64_t mlp_bwd_tc_workspace_bytes(int64_t M);

@@ -129,7 +129,12 @@ constexpr int kTapeSlotPe = 0, kTapeSlotPed = 1, kTapeSlotH = 2, kTapeSlotFeat =
 constexpr int kTapeFwdSlots = 40;
 // Backward slots (written by the dgrad chain): dZv (2), dFEAT (4), dZ7 .. dZ0 (4 each).
 constexpr int kTapeBwdSlotZv = 0, kTapeBwdSlotFeat = 2, kTapeBwdSlotZ = 6;   // dZ_l at kTapeBwdSlotZ + 4*(7-l)
-constexpr int kTapeBwdSlots = 38;
+constexpr int kTapeBwdSlotG = 38;      // g_raw as a bf16 image: columns 0..2 = d/d rgb_raw, 3 = d/d sigma_raw (chunk 0 only is defined)
+constexpr int kTapeBwdSlots = 39;
+// ReLU bitmasks of the forward activations: per tile 68 units of 32 columns (H0..H7: 8 units each, HV: 4), per
+// unit 128 rows x u32.  Bit i (i < 16) = column 2i of the unit, bit 16+i = column 2i+1 (set = activation > 0).
+constexpr int kMaskUnits = 68, kMaskUnitHv = 64;
+constexpr int kMaskTileBytes = kMaskUnits * 128 * 4;
 
 // swizzled byte offset of element (row r, column k in [0,64)) inside a chunk / activation K-block
 FN_HD uint32_t sw128_offset(uint32_t r, uint32_t k) {

@@ -29,8 +29,9 @@ constexpr uint32_t kWgSmem = kWgOffBar + (2 * kWgStages + 1) * 8 + 16 + 1024;
 struct WgradParams {
   const uint8_t* dz; int64_t dz_tile_stride; int dz_slot0; int n_kb;   // dZ images: tile t, K-block kb at dz + t*stride + (slot0+kb)*16K
   const uint8_t* x;  int64_t x_tile_stride;  int x_slot0;  int x_kb;   // X images
-  float* dw; int64_t ld;                                               // dW[n][k] at dw[n*ld + k]
-  int n_valid;                                                         // k < n_valid columns are written (63 / 27 / 64*x_kb)
+  float* dw; int64_t ld_n, ld_k;                                       // dW[n][k] at dw[n*ld_n + (k - k0)*ld_k]
+  int k0, n_valid;                                                     // columns k0 <= k < n_valid are written (63 / 27 / 64*x_kb)
+  float* bias;                                                         // nullable: bias[n] += sum_m dZ[m][n] (column sums of the A operand)
   int64_t ntiles;
 };
 
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const WgradParams P)
   const uint32_t stage_bytes = (uint32_t)(P.n_kb + P.x_kb) * kHalfImg;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    // a stage is released by the MMA commit and, when bias sums are wanted, by the four epilogue warps that read it
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), P.bias ? 5 : 1); }
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
@@ -114,20 +116,56 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const WgradParams P)
       __syncwarp();
     }
   } else if (nhalf > 0) {
-    // epilogue: TMEM lane = output feature (row of dW), columns = input features
     const uint32_t q = (uint32_t)warp & 3u;
+    if (P.bias != nullptr) {
+      // bias gradients while the MMAs stream: thread e sums the column pair (kb = e / 32, columns 2p, 2p+1) of
+      // the dZ half-images of every stage; a warp reads one 128-byte image row per instruction (conflict-free)
+      const int e = (int)threadIdx.x - 64, kb = e >> 5;
+      const uint32_t p = (uint32_t)e & 31u;
+      const bool active = kb < P.n_kb;
+      float b0 = 0.0f, b1 = 0.0f;
+      for (int64_t it = 0; it < nhalf; ++it) {
+        const uint32_t s = (uint32_t)(it % kWgStages);
+        mbar_wait(bar_full(s), (uint32_t)((it / kWgStages) & 1));
+        if (active) {
+          const uint8_t* img = base_ptr + s * kWgStageBytes + (uint32_t)kb * kHalfImg + (p & 3u) * 4u;
+#pragma unroll 8
+          for (uint32_t r = 0; r < 64; ++r) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(img + r * 128u + (((p >> 2) ^ (r & 7u)) << 4));
+            b0 += __uint_as_float(w << 16);
+            b1 += __uint_as_float(w & 0xFFFF0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty(s));
+      }
+      if (active) {
+        atomicAdd(P.bias + kb * 64 + 2 * (int)p, b0);
+        atomicAdd(P.bias + kb * 64 + 2 * (int)p + 1, b1);
+      }
+    }
+    // epilogue: TMEM lane = output feature (row of dW), columns = input features
+    const bool vec = P.ld_k == 1 && P.k0 == 0 && (P.ld_n & 3) == 0 && (P.n_valid & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(P.dw) & 15u) == 0;
     mbar_wait(bar_done, 0);
     tc_fence_after();
     for (int mb = 0; mb < n_blocks; ++mb) {
       const int n = mb * 128 + (int)(q * 32u) + lane;
-      float* out = P.dw + (int64_t)n * P.ld;
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      float* out = P.dw + (int64_t)n * P.ld_n;
+      for (int c0 = 0; c0 < N && c0 < P.n_valid; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mb * 256u + (uint32_t)c0, v);
         tmem_ld_wait();
+        if (vec) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < P.n_valid) atomicAdd(out + c0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            if (c0 + j < P.n_valid)
+              red_add_v4(out + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j >= P.k0 && c0 + j < P.n_valid) atomicAdd(out + (int64_t)(c0 + j - P.k0) * P.ld_k, __uint_as_float(v[j]));
+        }
       }
     }
     tc_fence_before();
@@ -156,91 +194,19 @@ int launch_wgrad_tc(const WgradParams& P, cudaStream_t s) {
   return check_launch("wgrad_tc");
 }
 
-// ---- bias and head gradients straight from the tape ---------------------------------------------------
-// One CTA per tile, 256 threads = columns.  Reads every dZ image once (HBM-bound) and adds the column
-// sums into the bias gradients; the two tiny heads (sigma: 256->1 on H7, rgb: 128->3 on HV) are fp32 dot
-// products against g_raw.
-__device__ __forceinline__ float tape_elem(const uint8_t* img, int r, int col) {   // image of 128 x 64, column col < 64
-  const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)col >> 3) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)col & 7u) * 2u;
-  const unsigned short b = *reinterpret_cast<const unsigned short*>(img + off);
-  return __uint_as_float((uint32_t)b << 16);
-}
+int launch_mlp_dgrad_tc(const void* packed, int cond, const float* g_raw, const uint32_t* mask_tape, uint8_t* bwd_tape,
+                        float* flat_grad, int64_t M, cudaStream_t s);
+int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cudaStream_t s);
 
-__global__ void __launch_bounds__(256) k_bias_heads_from_tape(const uint8_t* __restrict__ fwd_tape, const uint8_t* __restrict__ bwd_tape,
-                                                              const float4* __restrict__ g_raw, float* __restrict__ flat_grad,
-                                                              int cond, int64_t M, int64_t ntiles) {
-  __shared__ float4 s_g[128];
-  const int n = threadIdx.x;
-  float bsum[10];                                     // dZ0..dZ7, dFEAT, dZv
-#pragma unroll
-  for (int i = 0; i < 10; ++i) bsum[i] = 0.0f;
-  float wa = 0.0f, wr0 = 0.0f, wr1 = 0.0f, wr2 = 0.0f, gs = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    __syncthreads();
-    if (n < 128) {
-      const int64_t g = tile * 128 + n;
-      s_g[n] = g < M ? g_raw[g] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    const uint8_t* ft = fwd_tape + (size_t)tile * kTapeFwdSlots * 16384;
-    const uint8_t* bt = bwd_tape + (size_t)tile * kTapeBwdSlots * 16384;
-    const int kb = n >> 6, col = n & 63;
-#pragma unroll 1
-    for (int l = 0; l < 8; ++l) {
-      const uint8_t* img = bt + (size_t)(kTapeBwdSlotZ + 4 * (7 - l) + kb) * 16384;
-      float a = 0.0f;
-      for (int r = 0; r < 128; ++r) a += tape_elem(img, r, col);
-      bsum[l] += a;
-    }
-    {
-      const uint8_t* img = bt + (size_t)(kTapeBwdSlotFeat + kb) * 16384;
-      const uint8_t* h7 = ft + (size_t)(kTapeSlotH + 28 + kb) * 16384;
-      float a = 0.0f, w = 0.0f;
-      for (int r = 0; r < 128; ++r) { a += tape_elem(img, r, col); w = fmaf(s_g[r].w, tape_elem(h7, r, col), w); }
-      bsum[8] += a; wa += w;
-    }
-    if (n < 128) {
-      const uint8_t* img = bt + (size_t)(kTapeBwdSlotZv + kb) * 16384;
-      const uint8_t* hv = ft + (size_t)(kTapeSlotHv + kb) * 16384;
-      float a = 0.0f;
-      for (int r = 0; r < 128; ++r) {
-        a += tape_elem(img, r, col);
-        const float h = tape_elem(hv, r, col);
-        const float4 gq = s_g[r];
-        wr0 = fmaf(gq.x, h, wr0); wr1 = fmaf(gq.y, h, wr1); wr2 = fmaf(gq.z, h, wr2);
-      }
-      bsum[9] += a;
-    }
-    if (n == 0) for (int r = 0; r < 128; ++r) { gs += s_g[r].w; g0 += s_g[r].x; g1 += s_g[r].y; g2 += s_g[r].z; }
-  }
-  for (int l = 0; l < 8; ++l) atomicAdd(flat_grad + flat_bias_offset(l, cond) + n, bsum[l]);
-  atomicAdd(flat_grad + flat_bias_offset(9, cond) + n, bsum[8]);
-  atomicAdd(flat_grad + flat_weight_offset(8, cond) + n, wa);
-  if (n < 128) {
-    atomicAdd(flat_grad + flat_bias_offset(10, cond) + n, bsum[9]);
-    atomicAdd(flat_grad + flat_weight_offset(11, cond) + n, wr0);
-    atomicAdd(flat_grad + flat_weight_offset(11, cond) + kWV + n, wr1);
-    atomicAdd(flat_grad + flat_weight_offset(11, cond) + 2 * kWV + n, wr2);
-  }
-  if (n == 0) {
-    atomicAdd(flat_grad + flat_bias_offset(8, cond), gs);
-    atomicAdd(flat_grad + flat_bias_offset(11, cond), g0);
-    atomicAdd(flat_grad + flat_bias_offset(11, cond) + 1, g1);
-    atomicAdd(flat_grad + flat_bias_offset(11, cond) + 2, g2);
-  }
-}
-
-int launch_mlp_dgrad_tc(const void* packed, int cond, const float* g_raw, const uint8_t* fwd_tape, uint8_t* bwd_tape,
-                        int64_t M, cudaStream_t s);
-
+// workspace: forward tape | backward tape | ReLU bitmasks | raw scratch
 int64_t mlp_bwd_tc_workspace_bytes(int64_t M) {
   const int64_t ntiles = (M + 127) / 128;
-  return ntiles * (int64_t)(kTapeFwdSlots + kTapeBwdSlots) * 16384 + ntiles * 128 * 16 + 4096;
+  return ntiles * ((int64_t)(kTapeFwdSlots + kTapeBwdSlots) * 16384 + kMaskTileBytes + 128 * 16) + 4096;
 }
 
-// Full bf16 tensor-core backward of one network query: forward with tape, dgrad chain, wgrad GEMMs, bias /
-// head reductions.  flat_grad += dL/dparams.  (Unconditioned networks; the conditioned variant uses the
-// fp32 path.)
+// Full bf16 tensor-core backward of one network query: forward with tape, dgrad chain, wgrad GEMMs (which
+// also sum the bias gradients) and the two head products.  flat_grad += dL/dparams.  (Unconditioned
+// networks; the conditioned variant uses the fp32 path.)
 int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws, int64_t ws_bytes, cudaStream_t s) {
   const int64_t M = a.R * a.S;
   if (M == 0) return 0;
@@ -248,41 +214,49 @@ int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, vo
   if (ws_bytes < mlp_bwd_tc_workspace_bytes(M)) return set_error(FNERF_ERR_WORKSPACE, "mlp_bwd_tc: workspace too small");
   uint8_t* fwd_tape = reinterpret_cast<uint8_t*>(ws);
   uint8_t* bwd_tape = fwd_tape + ntiles * (int64_t)kTapeFwdSlots * 16384;
-  float* raw_scratch = reinterpret_cast<float*>(bwd_tape + ntiles * (int64_t)kTapeBwdSlots * 16384);
+  uint32_t* mask_tape = reinterpret_cast<uint32_t*>(bwd_tape + ntiles * (int64_t)kTapeBwdSlots * 16384);
+  float* raw_scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(mask_tape) + ntiles * (int64_t)kMaskTileBytes);
   const int cond = 0;
   MlpArgs fa = a;
   fa.raw = raw_scratch;
   int rc;
-  if ((rc = launch_mlp_tc_save(fa, fwd_tape, s))) return rc;
-  if ((rc = launch_mlp_dgrad_tc(a.packed, cond, g_raw, fwd_tape, bwd_tape, M, s))) return rc;
+  if ((rc = launch_mlp_tc_tape(fa, fwd_tape, mask_tape, s))) return rc;
+  if ((rc = launch_mlp_dgrad_tc(a.packed, cond, g_raw, mask_tape, bwd_tape, flat_grad, M, s))) return rc;
 
   const int64_t fstride = (int64_t)kTapeFwdSlots * 16384, bstride = (int64_t)kTapeBwdSlots * 16384;
-  auto wg = [&](int dz_slot, int n_kb, int x_slot, int x_kb, float* dw, int64_t ld, int n_valid) {
+  auto wg = [&](const uint8_t* dz, int64_t dz_stride, int dz_slot, int n_kb, const uint8_t* x, int64_t x_stride, int x_slot,
+                int x_kb, float* dw, int64_t ld_n, int64_t ld_k, int k0, int n_valid, float* bias) {
     WgradParams P;
-    P.dz = bwd_tape; P.dz_tile_stride = bstride; P.dz_slot0 = dz_slot; P.n_kb = n_kb;
-    P.x = fwd_tape; P.x_tile_stride = fstride; P.x_slot0 = x_slot; P.x_kb = x_kb;
-    P.dw = dw; P.ld = ld; P.n_valid = n_valid; P.ntiles = ntiles;
+    P.dz = dz; P.dz_tile_stride = dz_stride; P.dz_slot0 = dz_slot; P.n_kb = n_kb;
+    P.x = x; P.x_tile_stride = x_stride; P.x_slot0 = x_slot; P.x_kb = x_kb;
+    P.dw = dw; P.ld_n = ld_n; P.ld_k = ld_k; P.k0 = k0; P.n_valid = n_valid; P.bias = bias; P.ntiles = ntiles;
     return launch_wgrad_tc(P, s);
   };
+  // dZ (backward tape) x forward activation
+  auto wz = [&](int dz_slot, int n_kb, int x_slot, int x_kb, float* dw, int64_t ld, int n_valid, float* bias) {
+    return wg(bwd_tape, bstride, dz_slot, n_kb, fwd_tape, fstride, x_slot, x_kb, dw, ld, 1, 0, n_valid, bias);
+  };
   auto gw = [&](int l) { return flat_grad + flat_weight_offset(l, cond); };
+  auto gb = [&](int l) { return flat_grad + flat_bias_offset(l, cond); };
   auto zslot = [&](int l) { return kTapeBwdSlotZ + 4 * (7 - l); };
   const int in5 = kPE + kW;
-  if ((rc = wg(zslot(0), 4, kTapeSlotPe, 1, gw(0), kPE, kPE))) return rc;
+  if ((rc = wz(zslot(0), 4, kTapeSlotPe, 1, gw(0), kPE, kPE, gb(0)))) return rc;
   for (int l = 1; l <= 7; ++l) {
     if (l == 5) {
-      if ((rc = wg(zslot(5), 4, kTapeSlotPe, 1, gw(5), in5, kPE))) return rc;
-      if ((rc = wg(zslot(5), 4, kTapeSlotH + 4 * 4, 4, gw(5) + kPE, in5, kW))) return rc;
+      if ((rc = wz(zslot(5), 4, kTapeSlotPe, 1, gw(5), in5, kPE, nullptr))) return rc;
+      if ((rc = wz(zslot(5), 4, kTapeSlotH + 4 * 4, 4, gw(5) + kPE, in5, kW, gb(5)))) return rc;
     } else {
-      if ((rc = wg(zslot(l), 4, kTapeSlotH + 4 * (l - 1), 4, gw(l), kW, kW))) return rc;
+      if ((rc = wz(zslot(l), 4, kTapeSlotH + 4 * (l - 1), 4, gw(l), kW, kW, gb(l)))) return rc;
     }
   }
-  if ((rc = wg(kTapeBwdSlotFeat, 4, kTapeSlotH + 28, 4, gw(9), kW, kW))) return rc;
-  if ((rc = wg(kTapeBwdSlotZv, 2, kTapeSlotFeat, 4, gw(10), kW + kPED, kW))) return rc;
-  if ((rc = wg(kTapeBwdSlotZv, 2, kTapeSlotPed, 1, gw(10) + kW, kW + kPED, kPED))) return rc;
-  int64_t blocks = ntiles < 4 * (int64_t)num_sms() ? ntiles : 4 * (int64_t)num_sms();
-  k_bias_heads_from_tape<<<(unsigned)blocks, 256, 0, s>>>(fwd_tape, bwd_tape, reinterpret_cast<const float4*>(g_raw), flat_grad,
-                                                         cond, M, ntiles);
-  return check_launch("mlp_bwd_tc");
+  if ((rc = wz(kTapeBwdSlotFeat, 4, kTapeSlotH + 28, 4, gw(9), kW, kW, gb(9)))) return rc;
+  if ((rc = wz(kTapeBwdSlotZv, 2, kTapeSlotFeat, 4, gw(10), kW + kPED, kW, gb(10)))) return rc;
+  if ((rc = wz(kTapeBwdSlotZv, 2, kTapeSlotPed, 1, gw(10) + kW, kW + kPED, kPED, nullptr))) return rc;
+  // heads: the "dZ" operand is a forward activation, the "X" operand the g_raw image (columns rgb, sigma)
+  //   rgb_linear.weight[c][n]  += sum_m HV[m][n] g_rgb[m][c]      alpha_linear.weight[0][n] += sum_m H7[m][n] g_sigma[m]
+  if ((rc = wg(fwd_tape, fstride, kTapeSlotHv, 2, bwd_tape, bstride, kTapeBwdSlotG, 1, gw(11), 1, kWV, 0, 3, nullptr))) return rc;
+  if ((rc = wg(fwd_tape, fstride, kTapeSlotH + 28, 4, bwd_tape, bstride, kTapeBwdSlotG, 1, gw(8), 1, 0, 3, 4, nullptr))) return rc;
+  return 0;
 }
 
 }  // namespace fnerf
@@ -293,6 +267,6 @@ extern "C" int fnerf_debug_wgrad_tc(const void* dz_img, int n_kb, const void* x_
   fnerf::WgradParams P;
   P.dz = reinterpret_cast<const uint8_t*>(dz_img); P.dz_tile_stride = (int64_t)n_kb * 16384; P.dz_slot0 = 0; P.n_kb = n_kb;
   P.x = reinterpret_cast<const uint8_t*>(x_img); P.x_tile_stride = (int64_t)x_kb * 16384; P.x_slot0 = 0; P.x_kb = x_kb;
-  P.dw = dw; P.ld = ld; P.n_valid = n_valid; P.ntiles = ntiles;
+  P.dw = dw; P.ld_n = ld; P.ld_k = 1; P.k0 = 0; P.n_valid = n_valid; P.bias = nullptr; P.ntiles = ntiles;
   return fnerf::launch_wgrad_tc(P, (cudaStream_t)stream);
 }

@@ -46,7 +46,7 @@ constexpr uint32_t kOffW = kOffPed + kKBlockBytes;              // weight stages
 constexpr uint32_t kOffHeads = kOffW + kStages * kBigChunkBytes;  // fp32 head weights (aux from kAuxWAlpha on)
 constexpr int kHeadFloats = kAuxFloats - kAuxWAlpha;
 constexpr uint32_t kOffBar = kOffHeads + kHeadFloats * 4;
-constexpr uint32_t kNumBars = 2 * kStages + 4 + 1 + 2;
+constexpr uint32_t kNumBars = 2 * kStages + 4 + 1 + 2 + 1;     // + tape-store drain barrier (training forward)
 constexpr uint32_t kTcSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;  // + tmem ptr + alignment slack
 static_assert(kOffBar % 8 == 0, "barrier alignment");
 static_assert(kTcSmemBytes <= 227 * 1024, "shared memory budget");
@@ -90,8 +90,19 @@ struct TcParams {
   const float* cond_proj; const int32_t* cond_index; int64_t C;
   float4* raw;
   int64_t M; int S; int64_t ntiles; int cond;
-  uint8_t* tape;   // kSave only: per tile kTapeFwdSlots K-block images (layout.h), the shared-memory bytes verbatim
+  uint8_t* tape;        // kSave only: per tile kTapeFwdSlots K-block images (layout.h), the shared-memory bytes verbatim
+  uint32_t* mask_tape;  // kSave only: per tile kMaskUnits x 128 ReLU bitmask words (layout.h)
 };
+
+// tape slot of the activation K-block that gated chunk c consumes (the output of the previous layer)
+__host__ __device__ constexpr int tape_slot_of_chunk(int c) {
+  const ChunkDesc d = chunk_desc(c);
+  return (d.layer == 10 ? kTapeSlotFeat : (d.layer == 9 ? kTapeSlotH + 28 : kTapeSlotH + 4 * (d.layer - 1))) + d.kb;
+}
+
+// two non-negative bf16 in one word -> bit 0 = (low half != 0), bit 16 = (high half != 0): adding 0x7FFF to a
+// non-negative bf16 (<= 0x7F80) sets bit 15 exactly when it is non-zero and never carries into the other half
+__device__ __forceinline__ uint32_t relu_bits(uint32_t packed) { return ((packed + 0x7FFF7FFFu) >> 15) & 0x00010001u; }
 
 // epilogue of one 32-column unit: TMEM -> (+rowbias) -> [ReLU] -> bf16 -> swizzled smem.  The layer
 // bias is already in the accumulator.  `chunk0` is the index (0 or 4) of the unit's first 16-byte
@@ -100,10 +111,11 @@ template <bool kRelu, bool kSigma, bool kCond>
 __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __restrict__ walpha_s,
                                               const float* __restrict__ rowbias, uint32_t act_row_addr,
                                               uint32_t chunk0, uint32_t row, float& sigma,
-                                              uint8_t* __restrict__ save_row = nullptr) {
+                                              uint32_t* __restrict__ mask_out = nullptr) {
   uint32_t v[32];
   tmem_ld32(taddr, v);
   tmem_ld_wait();
+  uint32_t mask = 0u;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {            // 16-byte chunk = 8 columns
     float x[8];
@@ -134,9 +146,11 @@ __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __res
     }
     const uint32_t c16 = chunk0 + (uint32_t)c;
     st_shared_v4(act_row_addr + ((c16 ^ (row & 7u)) << 4), p0, p1, p2, p3);
-    if (save_row != nullptr)   // training tape: the same 16 bytes at the same swizzled offset of the K-block image
-      *reinterpret_cast<uint4*>(save_row + ((c16 ^ (row & 7u)) << 4)) = make_uint4(p0, p1, p2, p3);
+    if (kRelu && mask_out != nullptr) {   // training tape: bit i = column 2i > 0, bit 16+i = column 2i+1 > 0
+      mask |= relu_bits(p0) << (4 * c) | relu_bits(p1) << (4 * c + 1) | relu_bits(p2) << (4 * c + 2) | relu_bits(p3) << (4 * c + 3);
+    }
   }
+  if (kRelu && mask_out != nullptr) *mask_out = mask;
 }
 
 __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
@@ -152,6 +166,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   auto bar_act = [&](int kb) { return bar0 + 8u * (2 * kStages + kb); };
   const uint32_t bar_pe = bar0 + 8u * (2 * kStages + 4);
   auto bar_acc = [&](int a) { return bar0 + 8u * (2 * kStages + 5 + a); };
+  const uint32_t bar_st = bar0 + 8u * (2 * kStages + 7);            // kSave: tape stores no longer read the activation tile
   const uint32_t tmem_slot = bar0 + 8u * kNumBars;
   float* heads_s = reinterpret_cast<float*>(base_ptr + kOffHeads);   // index with (kAux* - kAuxWAlpha)
 
@@ -168,6 +183,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     mbar_init(bar_pe, 256);                                       // encoding groups 0 and 1
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
+    mbar_init(bar_st, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -211,7 +227,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     {
       constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256);
       constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
+      // Training forward (kSave): lane 0 also streams every finished K-block image (encodings, H0..H7, feature,
+      // view-layer output) from shared memory to the tape with one 16 KB bulk store, issued where the
+      // issuer has just seen the image's act-ready barrier; after a layer's last MMA it drains the stores
+      // (wait_group.read) and signals bar_st, which the epilogue that overwrites the tile waits for.
       uint32_t wc = 0, act_cnt = 0, tile_cnt = 0;
+      [[maybe_unused]] uint32_t hv_cnt = 0;     // kSave: K-blocks 0/1 see one extra act-ready phase per tile (HV image)
       [[maybe_unused]] uint32_t tslot = 0;   // tracer: slots [0,256): (before waits, operands ready, issued) per chunk
       const uint64_t desc_act = umma_desc_sw128(base + kOffAct);
       const uint64_t desc_pe = umma_desc_sw128(base + kOffPe);
@@ -221,6 +242,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
       const uint32_t acc_addr[2] = {tmem_u, tmem_u + 256};
       for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride, ++tile_cnt) {
         mbar_wait(bar_pe, tile_cnt & 1u);
+        [[maybe_unused]] uint8_t* tape_tile = kSave ? P.tape + (size_t)tile * kTapeFwdSlots * kKBlockBytes : nullptr;
+        if (kSave && lane == 0) {
+          bulk_s2g(tape_tile + kTapeSlotPe * kKBlockBytes, base + kOffPe, kKBlockBytes);
+          bulk_s2g(tape_tile + kTapeSlotPed * kKBlockBytes, base + kOffPed, kKBlockBytes);
+          bulk_commit();
+        }
         bool w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full(wc % kStages), (wc / kStages) & 1u));
         bool a_ready = true;
 #pragma unroll
@@ -228,7 +255,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const MmaChunk op = mma_chunk(c);
           const uint32_t s = wc % kStages;
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
-          if (op.gated && !a_ready) mbar_wait(bar_act(op.kb), act_cnt & 1u);
+          if (op.gated && !a_ready) mbar_wait(bar_act(op.kb), (act_cnt + ((kSave && op.kb < 2) ? hv_cnt : 0u)) & 1u);
+          if (kSave && op.gated) {
+            if (lane == 0) {
+              bulk_s2g(tape_tile + (size_t)tape_slot_of_chunk(c) * kKBlockBytes, base + kOffAct + (uint32_t)op.kb * kKBlockBytes, kKBlockBytes);
+              bulk_commit();
+            }
+          }
           if (!w_ready) mbar_wait(bar_full(s), (wc / kStages) & 1u);
           tc_fence_after();
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
@@ -237,7 +270,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full((wc + 1) % kStages), ((wc + 1) / kStages) & 1u));
           if (c + 1 < kNumChunks) {
             const MmaChunk nx = mma_chunk(c + 1);
-            a_ready = nx.gated ? __all_sync(0xffffffffu, mbar_test_wait(bar_act(nx.kb), act_next & 1u)) : true;
+            a_ready = nx.gated ? __all_sync(0xffffffffu, mbar_test_wait(bar_act(nx.kb), (act_next + ((kSave && nx.kb < 2) ? hv_cnt : 0u)) & 1u)) : true;
           } else {
             a_ready = true;
           }
@@ -257,11 +290,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
             if (op.commit_acc) umma_commit(bar_acc(op.acc));
           }
           __syncwarp();
+          if (kSave && op.commit_acc && chunk_desc(c).layer != 0) {   // this layer read the activation tile: drain its stores
+            if (lane == 0) { bulk_wait_read<0>(); mbar_arrive(bar_st); }
+            __syncwarp();
+          }
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
           act_cnt = act_next;
           ++wc;
         }
+        if (kSave) {                 // view-layer output image (K-blocks 0, 1 of the activation tile)
+          mbar_wait(bar_act(0), (act_cnt + hv_cnt) & 1u);
+          mbar_wait(bar_act(1), (act_cnt + hv_cnt) & 1u);
+          if (lane == 0) {
+            bulk_s2g(tape_tile + (size_t)kTapeSlotHv * kKBlockBytes, base + kOffAct, 2 * kKBlockBytes);
+            bulk_commit();
+            bulk_wait_read<0>();
+            mbar_arrive(bar_st);
+          }
+          __syncwarp();
+          ++hv_cnt;
+        }
       }
+      if (kSave && lane == 0) bulk_wait_all<0>();
     }
   } else {
     // ================================ workers: encodings + epilogues ===============================
@@ -270,14 +320,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     const uint32_t row = q * 32u + (uint32_t)lane;
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     uint32_t acc_cnt[2] = {0u, 0u};
+    [[maybe_unused]] uint32_t wtile_n = 0;                         // tiles this CTA has finished
     [[maybe_unused]] uint32_t wtile = 0, wslot = 256 + grp * 64;   // tracer: 64 slots per group from 256
+    [[maybe_unused]] uint32_t st_cnt = 0;                          // kSave: bar_st phases consumed
     const uint32_t act_row = base + kOffAct + row * 128u;
     uint8_t* ped_row_ptr = base_ptr + kOffPed + row * 128u;
     for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride) {
       const int64_t g = tile * kTileM + row;
       const int64_t gc = g < P.M ? g : P.M - 1;
       const int64_t ray = gc / P.S;
-      uint8_t* tape_row = kSave ? P.tape + (size_t)tile * kTapeFwdSlots * kKBlockBytes + row * 128u : nullptr;
+      [[maybe_unused]] uint32_t* mask_row = kSave ? P.mask_tape + (size_t)tile * (kMaskUnits * 128) + row : nullptr;
       // ---- positional encodings (A.3): sincos once, then double-angle recurrence per octave -----
       if (grp == 0) {
         const float zv = P.z[gc];
@@ -304,7 +356,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const uint4 pk = make_uint4(pack_bf16(f[c16 * 8 + 0], f[c16 * 8 + 1]), pack_bf16(f[c16 * 8 + 2], f[c16 * 8 + 3]),
                                       pack_bf16(f[c16 * 8 + 4], f[c16 * 8 + 5]), pack_bf16(f[c16 * 8 + 6], f[c16 * 8 + 7]));
           st_shared_v4(pe_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
-          if (kSave) *reinterpret_cast<uint4*>(tape_row + kTapeSlotPe * kKBlockBytes + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_pe);
@@ -331,15 +382,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         }
         const uint32_t ped_row = base + kOffPed + row * 128u;
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-          if (c16 < 4) {
-            pk = make_uint4(pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
-                            pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
-            st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
-          }
-          // the saved image is complete (zeros in columns 32..63): wgrad multiplies all 64 columns
-          if (kSave) *reinterpret_cast<uint4*>(tape_row + kTapeSlotPed * kKBlockBytes + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
+        for (int c16 = 0; c16 < 4; ++c16) {
+          // columns 32..63 of the tile are never multiplied by the forward (and hold the rgb partials at the end
+          // of a tile); the taped image carries them along, wgrad only writes out the first 27 columns
+          const uint4 pk = make_uint4(pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
+                                      pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
+          st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_pe);
@@ -360,6 +408,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         FN_TRACE(wtile == 2 && row == 0, wslot++);
         ++acc_cnt[a];
         tc_fence_after();
+        if (kSave && (step > 0 || wtile_n > 0)) {      // the tape stores of the tile's previous content have drained
+          mbar_wait(bar_st, st_cnt & 1u);
+          ++st_cnt;
+        }
         const uint32_t tacc = tmem_row + (uint32_t)a * 256u;
 #pragma unroll 1
         for (int round = 0; round < 2; ++round) {
@@ -367,7 +419,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const uint32_t kb = unit >> 1, half = unit & 1u;
           const uint32_t col0 = unit * 32u;
           const uint32_t dst = act_row + kb * kKBlockBytes;
-          uint8_t* sv = kSave ? tape_row + (size_t)(kTapeSlotH + 4 * step + (int)kb) * kKBlockBytes : nullptr;   // H0..H7, FEAT
+          uint32_t* sv = kSave ? mask_row + (step * 8 + (int)unit) * 128 : nullptr;   // ReLU bitmask word (steps 0..7)
           if (step == 8)
             epilogue_unit<false, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma, sv);
           else if (step == 7)
@@ -403,17 +455,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           c1 = fmaf(h, wrgb[kWV + col], c1);
           c2 = fmaf(h, wrgb[2 * kWV + col], c2);
         }
-        if (kSave) {             // HV image: 2 K-blocks of 64 columns; this group's 32 columns = 4 chunks
-          uint8_t* hv_row = tape_row + (size_t)(kTapeSlotHv + (int)(grp >> 1)) * kKBlockBytes;
+        if (kSave) {             // HV image -> K-blocks 0, 1 of the (now idle) activation tile; this group's 32 columns = 4 chunks
+          mbar_wait(bar_st, st_cnt & 1u);     // feature image stores have drained
+          ++st_cnt;
+          uint32_t mask = 0u;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint4 pk = make_uint4(pack_bf16_relu(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])),
                                         pack_bf16_relu(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])),
                                         pack_bf16_relu(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])),
                                         pack_bf16_relu(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])));
+            mask |= relu_bits(pk.x) << (4 * c) | relu_bits(pk.y) << (4 * c + 1) | relu_bits(pk.z) << (4 * c + 2) | relu_bits(pk.w) << (4 * c + 3);
             const uint32_t c16 = (grp & 1u) * 4u + (uint32_t)c;
-            *reinterpret_cast<uint4*>(hv_row + ((c16 ^ (row & 7u)) << 4)) = pk;
+            st_shared_v4(act_row + (grp >> 1) * kKBlockBytes + ((c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
           }
+          mask_row[(kMaskUnitHv + (int)grp) * 128] = mask;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_act((int)(grp >> 1)));
         }
         tc_fence_before();
         // partials of groups 1..3 park in the unused upper half (logical chunks 5..7) of this row of
@@ -433,6 +492,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         }
       }
       ++wtile;
+      ++wtile_n;
     }
   }
 
@@ -452,8 +512,9 @@ extern "C" int fnerf_debug_set_trace(long long* buf) {
 #endif
 
 // tape == nullptr: render path.  tape != nullptr: training forward, every intermediate activation is also
-// written to the tape as K-block images (mlp_bwd_tc.cu consumes them).
-int launch_mlp_tc_save(const MlpArgs& a, uint8_t* tape, cudaStream_t s) {
+// streamed to the tape as K-block images plus one ReLU bitmask word per row and 32-column unit
+// (mlp_dgrad_tc.cu / mlp_bwd_tc.cu consume them).
+int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cudaStream_t s) {
   const int64_t M = a.R * a.S;
   if (M == 0) return 0;
   static bool attr_done[64][2] = {{false}};
@@ -472,7 +533,7 @@ int launch_mlp_tc_save(const MlpArgs& a, uint8_t* tape, cudaStream_t s) {
   P.cond_proj = a.cond_proj; P.cond_index = a.cond_index; P.C = a.C;
   P.raw = reinterpret_cast<float4*>(a.raw);
   P.M = M; P.S = (int)a.S; P.ntiles = (M + kTileM - 1) / kTileM; P.cond = a.cond;
-  P.tape = tape;
+  P.tape = tape; P.mask_tape = mask_tape;
   int64_t blocks = num_sms();
   if (blocks > P.ntiles) blocks = P.ntiles;
   if (sv) k_mlp_tc<true><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
@@ -480,6 +541,6 @@ int launch_mlp_tc_save(const MlpArgs& a, uint8_t* tape, cudaStream_t s) {
   return check_launch("mlp_tc");
 }
 
-int launch_mlp_tc(const MlpArgs& a, cudaStream_t s) { return launch_mlp_tc_save(a, nullptr, s); }
+int launch_mlp_tc(const MlpArgs& a, cudaStream_t s) { return launch_mlp_tc_tape(a, nullptr, nullptr, s); }
 
 }  // namespace fnerf
