@@ -157,6 +157,36 @@ int fnerf_mlp_bwd(int precision, const void* packed, int cond, const float* rays
   return launch_mlp_bwd_fp32(a, g_raw, flat_grad, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int64_t fnerf_mlp_tape_bytes(int64_t R, int64_t S) { return mlp_tape_bytes(R * S); }
+int64_t fnerf_mlp_bwd_tape_workspace_bytes(int64_t R, int64_t S) { return mlp_bwd_from_tape_workspace_bytes(R * S); }
+
+int fnerf_mlp_fwd_tape(const void* packed, int cond, const float* rays_o, const float* rays_d, const float* viewdirs,
+                       const float* z, const float* cond_proj, const int32_t* cond_index, int64_t C, float* raw,
+                       void* tape, int64_t tape_bytes, int64_t R, int64_t S, fnerf_stream_t stream) {
+  int rc = validate_mlp("mlp_fwd_tape", FNERF_PRECISION_BF16, packed, cond, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, raw, R, S);
+  if (rc != 0 || R == 0) return rc;
+  FN_REQUIRE(!cond, FNERF_ERR_ARG, "mlp_fwd_tape: conditioned networks train through fnerf_mlp_bwd (fp32 chain)");
+  FN_REQUIRE(tape != nullptr, FNERF_ERR_NULL, "mlp_fwd_tape: null tape");
+  FN_REQUIRE(FN_ALIGNED16(tape), FNERF_ERR_ALIGN, "mlp_fwd_tape: tape must be 16-byte aligned");
+  FN_REQUIRE(tape_bytes >= mlp_tape_bytes(R * S), FNERF_ERR_WORKSPACE, "mlp_fwd_tape: tape too small");
+  MlpArgs a{packed, 0, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, raw, R, S};
+  return launch_mlp_fwd_tape(a, tape, (cudaStream_t)stream);
+}
+
+int fnerf_mlp_bwd_tape(const void* packed, int cond, const float* g_raw, const void* tape, int64_t tape_bytes,
+                       float* flat_grad, void* workspace, int64_t workspace_bytes, int64_t R, int64_t S,
+                       fnerf_stream_t stream) {
+  FN_REQUIRE(R >= 0 && S >= 1, FNERF_ERR_SIZE, "mlp_bwd_tape: bad R=%lld S=%lld", (long long)R, (long long)S);
+  if (R == 0) return 0;
+  FN_REQUIRE(!cond, FNERF_ERR_ARG, "mlp_bwd_tape: conditioned networks train through fnerf_mlp_bwd (fp32 chain)");
+  FN_REQUIRE(packed && g_raw && tape && flat_grad && workspace, FNERF_ERR_NULL, "mlp_bwd_tape: null pointer");
+  FN_REQUIRE(FN_ALIGNED16(packed) && FN_ALIGNED16(g_raw) && FN_ALIGNED16(tape) && FN_ALIGNED16(workspace), FNERF_ERR_ALIGN,
+             "mlp_bwd_tape: packed / g_raw / tape / workspace must be 16-byte aligned");
+  FN_REQUIRE(tape_bytes >= mlp_tape_bytes(R * S), FNERF_ERR_WORKSPACE, "mlp_bwd_tape: tape too small");
+  FN_REQUIRE(workspace_bytes >= mlp_bwd_from_tape_workspace_bytes(R * S), FNERF_ERR_WORKSPACE, "mlp_bwd_tape: workspace too small");
+  return launch_mlp_bwd_from_tape(packed, 0, g_raw, tape, flat_grad, workspace, R * S, (cudaStream_t)stream);
+}
+
 int fnerf_composite_fwd(const float* raw, const float* z, const float* dnorm, const float* raw_noise,
                         float* rgb, float* depth, float* acc, float* disp, float* weights, int64_t R,
                         int64_t S, int white_bkgd, fnerf_stream_t stream) {
@@ -195,6 +225,8 @@ int fnerf_render_rays(const fnerf_render_args* a, fnerf_stream_t stream) {
              "render_rays: null output");
   FN_REQUIRE(Nf == 0 || (a->packed_fine && a->u_fine), FNERF_ERR_NULL, "render_rays: fine pass needs packed_fine and u_fine");
   FN_REQUIRE(a->workspace != nullptr, FNERF_ERR_NULL, "render_rays: null workspace");
+  FN_REQUIRE((!a->tape_coarse && !a->tape_fine) || (a->precision == FNERF_PRECISION_BF16 && !a->cond), FNERF_ERR_ARG,
+             "render_rays: training tapes need the bf16 path and an unconditioned network");
   FN_REQUIRE(FN_ALIGNED16(a->workspace), FNERF_ERR_ALIGN, "render_rays: workspace must be 16-byte aligned");
   const RenderWorkspace L = render_layout(R, Nc, Nf);
   FN_REQUIRE(a->workspace_bytes >= L.total, FNERF_ERR_WORKSPACE, "render_rays: workspace %lld < %lld",
@@ -217,8 +249,11 @@ int fnerf_render_rays(const fnerf_render_args* a, fnerf_stream_t stream) {
   if ((rc = fnerf_ray_setup(a->rays_d, viewdirs, dnorm, R, stream))) return rc;
   if ((rc = fnerf_stratified(a->near, a->far, a->t_vals, a->u_strat, z_c, R, Nc, a->lindisp, stream))) return rc;
   if (a->ev_coarse_start) cudaEventRecord((cudaEvent_t)a->ev_coarse_start, s);
-  if ((rc = fnerf_mlp_fwd(a->precision, a->packed_coarse, a->cond, a->rays_o, a->rays_d, viewdirs, z_c,
-                          a->cond_proj_coarse, a->cond_index, a->C, raw_c, R, Nc, stream))) return rc;
+  if (a->tape_coarse) {
+    if ((rc = fnerf_mlp_fwd_tape(a->packed_coarse, a->cond, a->rays_o, a->rays_d, viewdirs, z_c, a->cond_proj_coarse,
+                                 a->cond_index, a->C, raw_c, a->tape_coarse, a->tape_coarse_bytes, R, Nc, stream))) return rc;
+  } else if ((rc = fnerf_mlp_fwd(a->precision, a->packed_coarse, a->cond, a->rays_o, a->rays_d, viewdirs, z_c,
+                                 a->cond_proj_coarse, a->cond_index, a->C, raw_c, R, Nc, stream))) return rc;
   if (a->ev_coarse_stop) cudaEventRecord((cudaEvent_t)a->ev_coarse_stop, s);
   if (Nf == 0) {
     if ((rc = fnerf_composite_fwd(raw_c, z_c, dnorm, nullptr, a->rgb, a->depth, a->acc, a->disp, a->weights_c ? weights_c : nullptr,
@@ -234,8 +269,11 @@ int fnerf_render_rays(const fnerf_render_args* a, fnerf_stream_t stream) {
   if ((rc = fnerf_importance(z_c, weights_c, a->u_fine, a->u_fine_row_stride, z_samples, z_f, nullptr, a->z_std,
                              R, Nc, Nf, stream))) return rc;
   if (a->ev_fine_start) cudaEventRecord((cudaEvent_t)a->ev_fine_start, s);
-  if ((rc = fnerf_mlp_fwd(a->precision, a->packed_fine, a->cond, a->rays_o, a->rays_d, viewdirs, z_f,
-                          a->cond_proj_fine, a->cond_index, a->C, raw_f, R, Nc + Nf, stream))) return rc;
+  if (a->tape_fine) {
+    if ((rc = fnerf_mlp_fwd_tape(a->packed_fine, a->cond, a->rays_o, a->rays_d, viewdirs, z_f, a->cond_proj_fine,
+                                 a->cond_index, a->C, raw_f, a->tape_fine, a->tape_fine_bytes, R, Nc + Nf, stream))) return rc;
+  } else if ((rc = fnerf_mlp_fwd(a->precision, a->packed_fine, a->cond, a->rays_o, a->rays_d, viewdirs, z_f,
+                                 a->cond_proj_fine, a->cond_index, a->C, raw_f, R, Nc + Nf, stream))) return rc;
   if (a->ev_fine_stop) cudaEventRecord((cudaEvent_t)a->ev_fine_stop, s);
   if ((rc = fnerf_composite_fwd(raw_f, z_f, dnorm, nullptr, a->rgb, a->depth, a->acc, a->disp, a->weights_f, R,
                                 Nc + Nf, a->white_bkgd, stream))) return rc;

@@ -65,6 +65,11 @@ int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cud
 
 int64_t mlp_bwd_workspace_bytes(int64_t R, int64_t S);
 int64_t mlp_bwd_tc_workspace_bytes(int64_t M);
+int64_t mlp_tape_bytes(int64_t M);                       // forward tape of one bf16 network query
+int64_t mlp_bwd_from_tape_workspace_bytes(int64_t M);
+int launch_mlp_fwd_tape(const MlpArgs& a, void* tape, cudaStream_t s);
+int launch_mlp_bwd_from_tape(const void* packed, int cond, const float* g_raw, const void* tape, float* flat_grad, void* ws,
+                             int64_t M, cudaStream_t s);
 int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws, int64_t ws_bytes, cudaStream_t s);
 int launch_mlp_bwd_fp32(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws,
                         int64_t ws_bytes, cudaStream_t s);

@@ -26,12 +26,22 @@ constexpr uint32_t kWgStageBytes = 8 * kHalfImg;   // up to 4 dZ + 4 X half-imag
 constexpr uint32_t kWgOffBar = kWgStages * kWgStageBytes;
 constexpr uint32_t kWgSmem = kWgOffBar + (2 * kWgStages + 1) * 8 + 16 + 1024;
 
-struct WgradParams {
+constexpr int kWgMaxJobs = 16;
+struct WgradJob {
   const uint8_t* dz; int64_t dz_tile_stride; int dz_slot0; int n_kb;   // dZ images: tile t, K-block kb at dz + t*stride + (slot0+kb)*16K
   const uint8_t* x;  int64_t x_tile_stride;  int x_slot0;  int x_kb;   // X images
   float* dw; int64_t ld_n, ld_k;                                       // dW[n][k] at dw[n*ld_n + (k - k0)*ld_k]
   int k0, n_valid;                                                     // columns k0 <= k < n_valid are written (63 / 27 / 64*x_kb)
   float* bias;                                                         // nullable: bias[n] += sum_m dZ[m][n] (column sums of the A operand)
+  int cta0, ncta;                                                      // the CTAs [cta0, cta0 + ncta) share this job's tiles (set by the launcher)
+};
+// One launch runs every weight-gradient product of a network backward side by side: each job owns a slice
+// of the grid proportional to the bytes it streams (the kernel is HBM-bound), so a CTA accumulates ONE
+// product over ntiles / ncta tiles and flushes one accumulator -- 12x fewer atomics than one launch per
+// product over the whole grid, and no per-product launch tail.
+struct WgradBatch {
+  WgradJob jobs[kWgMaxJobs];
+  int njobs;
   int64_t ntiles;
 };
 
@@ -45,7 +55,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {   // A
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const WgradParams P) {
+__global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const WgradBatch B) {
+  int job = 0;
+  for (int j = 1; j < B.njobs; ++j)
+    if ((int)blockIdx.x >= B.jobs[j].cta0) job = j;
+  const WgradJob& P = B.jobs[job];
+  const int64_t tile0 = (int)blockIdx.x - P.cta0, tile_step = P.ncta;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -72,13 +87,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const WgradParams P)
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kWgOffBar + 8 * (2 * kWgStages + 1));
 
   int64_t my_tiles = 0;
-  for (int64_t t = blockIdx.x; t < P.ntiles; t += gridDim.x) ++my_tiles;
+  for (int64_t t = tile0; t < B.ntiles; t += tile_step) ++my_tiles;
   const int64_t nhalf = 2 * my_tiles;               // pipeline items: half tiles
 
   if (warp == 0) {
     if (lane == 0) {
       int64_t it = 0;
-      for (int64_t t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+      for (int64_t t = tile0; t < B.ntiles; t += tile_step) {
         for (int h = 0; h < 2; ++h, ++it) {
           const uint32_t s = (uint32_t)(it % kWgStages);
           mbar_wait(bar_empty(s), (uint32_t)((it / kWgStages) & 1) ^ 1u);
@@ -178,8 +193,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const WgradParams P)
   }
 }
 
-int launch_wgrad_tc(const WgradParams& P, cudaStream_t s) {
-  if (P.ntiles == 0) return 0;
+// Assigns grid slices (cost = K-block images streamed per tile) and launches.
+int launch_wgrad_tc(WgradBatch& B, cudaStream_t s) {
+  if (B.ntiles == 0 || B.njobs == 0) return 0;
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -188,9 +204,28 @@ int launch_wgrad_tc(const WgradParams& P, cudaStream_t s) {
     if (e != cudaSuccess) return set_error((int)e, "wgrad_tc attr: %s", cudaGetErrorString(e));
     attr_done[dev] = true;
   }
-  int64_t blocks = num_sms();
-  if (blocks > P.ntiles) blocks = P.ntiles;
-  k_wgrad_tc<<<(unsigned)blocks, kWgThreads, kWgSmem, s>>>(P);
+  const int sms = num_sms();
+  if (B.njobs > kWgMaxJobs || B.njobs > sms) return set_error(FNERF_ERR_ARG, "wgrad_tc: too many jobs");
+  int total_cost = 0, used = 0;
+  for (int j = 0; j < B.njobs; ++j) total_cost += B.jobs[j].n_kb + B.jobs[j].x_kb;
+  for (int j = 0; j < B.njobs; ++j) {
+    int n = (B.jobs[j].n_kb + B.jobs[j].x_kb) * sms / total_cost;
+    B.jobs[j].ncta = n < 1 ? 1 : n;
+    used += B.jobs[j].ncta;
+  }
+  for (int cost = 8; used < sms && cost > 0; --cost)          // leftover CTAs go to the heaviest jobs first
+    for (int j = 0; j < B.njobs && used < sms; ++j)
+      if (B.jobs[j].n_kb + B.jobs[j].x_kb == cost) { ++B.jobs[j].ncta; ++used; }
+  while (used > sms)                                          // (only if rounding up the tiny jobs overshot)
+    for (int j = 0; j < B.njobs && used > sms; ++j)
+      if (B.jobs[j].ncta > 1) { --B.jobs[j].ncta; --used; }
+  int cta = 0;
+  for (int j = 0; j < B.njobs; ++j) {
+    if ((int64_t)B.jobs[j].ncta > B.ntiles) B.jobs[j].ncta = (int)B.ntiles;
+    B.jobs[j].cta0 = cta;
+    cta += B.jobs[j].ncta;
+  }
+  k_wgrad_tc<<<(unsigned)cta, kWgThreads, kWgSmem, s>>>(B);
   return check_launch("wgrad_tc");
 }
 
@@ -198,39 +233,46 @@ int launch_mlp_dgrad_tc(const void* packed, int cond, const float* g_raw, const 
                         float* flat_grad, int64_t M, cudaStream_t s);
 int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cudaStream_t s);
 
-// workspace: forward tape | backward tape | ReLU bitmasks | raw scratch
-int64_t mlp_bwd_tc_workspace_bytes(int64_t M) {
+// forward tape of one network query: K-block images of every tile, then the ReLU bitmask words of every tile
+int64_t mlp_tape_bytes(int64_t M) {
   const int64_t ntiles = (M + 127) / 128;
-  return ntiles * ((int64_t)(kTapeFwdSlots + kTapeBwdSlots) * 16384 + kMaskTileBytes + 128 * 16) + 4096;
+  return ntiles * ((int64_t)kTapeFwdSlots * 16384 + kMaskTileBytes);
+}
+int64_t mlp_bwd_from_tape_workspace_bytes(int64_t M) { return (M + 127) / 128 * (int64_t)kTapeBwdSlots * 16384; }
+// recomputing backward: forward tape | backward tape | raw scratch
+int64_t mlp_bwd_tc_workspace_bytes(int64_t M) {
+  return mlp_tape_bytes(M) + mlp_bwd_from_tape_workspace_bytes(M) + (M + 127) / 128 * 128 * 16 + 4096;
 }
 
-// Full bf16 tensor-core backward of one network query: forward with tape, dgrad chain, wgrad GEMMs (which
-// also sum the bias gradients) and the two head products.  flat_grad += dL/dparams.  (Unconditioned
-// networks; the conditioned variant uses the fp32 path.)
-int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  const int64_t M = a.R * a.S;
+int launch_mlp_fwd_tape(const MlpArgs& a, void* tape, cudaStream_t s) {
+  const int64_t ntiles = (a.R * a.S + 127) / 128;
+  uint8_t* t = reinterpret_cast<uint8_t*>(tape);
+  return launch_mlp_tc_tape(a, t, reinterpret_cast<uint32_t*>(t + ntiles * (int64_t)kTapeFwdSlots * 16384), s);
+}
+
+// bf16 tensor-core backward of one network query from its forward tape: dgrad chain, then every
+// weight-gradient product (which also sums the bias gradients) and the two head products in one grouped
+// launch.  flat_grad += dL/dparams.  (Unconditioned networks; the conditioned variant uses the fp32 path.)
+int launch_mlp_bwd_from_tape(const void* packed, int cond, const float* g_raw, const void* tape, float* flat_grad, void* ws,
+                             int64_t M, cudaStream_t s) {
   if (M == 0) return 0;
   const int64_t ntiles = (M + 127) / 128;
-  if (ws_bytes < mlp_bwd_tc_workspace_bytes(M)) return set_error(FNERF_ERR_WORKSPACE, "mlp_bwd_tc: workspace too small");
-  uint8_t* fwd_tape = reinterpret_cast<uint8_t*>(ws);
-  uint8_t* bwd_tape = fwd_tape + ntiles * (int64_t)kTapeFwdSlots * 16384;
-  uint32_t* mask_tape = reinterpret_cast<uint32_t*>(bwd_tape + ntiles * (int64_t)kTapeBwdSlots * 16384);
-  float* raw_scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(mask_tape) + ntiles * (int64_t)kMaskTileBytes);
-  const int cond = 0;
-  MlpArgs fa = a;
-  fa.raw = raw_scratch;
+  const uint8_t* fwd_tape = reinterpret_cast<const uint8_t*>(tape);
+  const uint32_t* mask_tape = reinterpret_cast<const uint32_t*>(fwd_tape + ntiles * (int64_t)kTapeFwdSlots * 16384);
+  uint8_t* bwd_tape = reinterpret_cast<uint8_t*>(ws);
   int rc;
-  if ((rc = launch_mlp_tc_tape(fa, fwd_tape, mask_tape, s))) return rc;
-  if ((rc = launch_mlp_dgrad_tc(a.packed, cond, g_raw, mask_tape, bwd_tape, flat_grad, M, s))) return rc;
+  if ((rc = launch_mlp_dgrad_tc(packed, cond, g_raw, mask_tape, bwd_tape, flat_grad, M, s))) return rc;
 
   const int64_t fstride = (int64_t)kTapeFwdSlots * 16384, bstride = (int64_t)kTapeBwdSlots * 16384;
+  WgradBatch B;
+  B.njobs = 0; B.ntiles = ntiles;
   auto wg = [&](const uint8_t* dz, int64_t dz_stride, int dz_slot, int n_kb, const uint8_t* x, int64_t x_stride, int x_slot,
                 int x_kb, float* dw, int64_t ld_n, int64_t ld_k, int k0, int n_valid, float* bias) {
-    WgradParams P;
+    WgradJob& P = B.jobs[B.njobs++];
     P.dz = dz; P.dz_tile_stride = dz_stride; P.dz_slot0 = dz_slot; P.n_kb = n_kb;
     P.x = x; P.x_tile_stride = x_stride; P.x_slot0 = x_slot; P.x_kb = x_kb;
-    P.dw = dw; P.ld_n = ld_n; P.ld_k = ld_k; P.k0 = k0; P.n_valid = n_valid; P.bias = bias; P.ntiles = ntiles;
-    return launch_wgrad_tc(P, s);
+    P.dw = dw; P.ld_n = ld_n; P.ld_k = ld_k; P.k0 = k0; P.n_valid = n_valid; P.bias = bias; P.cta0 = 0; P.ncta = 1;
+    return 0;
   };
   // dZ (backward tape) x forward activation
   auto wz = [&](int dz_slot, int n_kb, int x_slot, int x_kb, float* dw, int64_t ld, int n_valid, float* bias) {
@@ -256,7 +298,21 @@ int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, vo
   //   rgb_linear.weight[c][n]  += sum_m HV[m][n] g_rgb[m][c]      alpha_linear.weight[0][n] += sum_m H7[m][n] g_sigma[m]
   if ((rc = wg(fwd_tape, fstride, kTapeSlotHv, 2, bwd_tape, bstride, kTapeBwdSlotG, 1, gw(11), 1, kWV, 0, 3, nullptr))) return rc;
   if ((rc = wg(fwd_tape, fstride, kTapeSlotH + 28, 4, bwd_tape, bstride, kTapeBwdSlotG, 1, gw(8), 1, 0, 3, 4, nullptr))) return rc;
-  return 0;
+  return launch_wgrad_tc(B, s);
+}
+
+// Recomputing variant: forward with tape into the workspace, then the backward above.
+int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws, int64_t ws_bytes, cudaStream_t s) {
+  const int64_t M = a.R * a.S;
+  if (M == 0) return 0;
+  if (ws_bytes < mlp_bwd_tc_workspace_bytes(M)) return set_error(FNERF_ERR_WORKSPACE, "mlp_bwd_tc: workspace too small");
+  uint8_t* tape = reinterpret_cast<uint8_t*>(ws);
+  uint8_t* bwd_ws = tape + (mlp_tape_bytes(M) + 1023) / 1024 * 1024;
+  MlpArgs fa = a;
+  fa.raw = reinterpret_cast<float*>(bwd_ws + mlp_bwd_from_tape_workspace_bytes(M));
+  int rc;
+  if ((rc = launch_mlp_fwd_tape(fa, tape, s))) return rc;
+  return launch_mlp_bwd_from_tape(a.packed, 0, g_raw, tape, flat_grad, bwd_ws, M, s);
 }
 
 }  // namespace fnerf
@@ -264,9 +320,11 @@ int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, vo
 // ---- debug entry (tests only): dw[n_kb*64, ld] += dZ^T X from two image buffers ---------------------
 extern "C" int fnerf_debug_wgrad_tc(const void* dz_img, int n_kb, const void* x_img, int x_kb, float* dw, int64_t ld,
                                     int n_valid, int64_t ntiles, void* stream) {
-  fnerf::WgradParams P;
+  fnerf::WgradBatch B;
+  B.njobs = 1; B.ntiles = ntiles;
+  fnerf::WgradJob& P = B.jobs[0];
   P.dz = reinterpret_cast<const uint8_t*>(dz_img); P.dz_tile_stride = (int64_t)n_kb * 16384; P.dz_slot0 = 0; P.n_kb = n_kb;
   P.x = reinterpret_cast<const uint8_t*>(x_img); P.x_tile_stride = (int64_t)x_kb * 16384; P.x_slot0 = 0; P.x_kb = x_kb;
-  P.dw = dw; P.ld_n = ld; P.ld_k = 1; P.k0 = 0; P.n_valid = n_valid; P.bias = nullptr; P.ntiles = ntiles;
-  return fnerf::launch_wgrad_tc(P, (cudaStream_t)stream);
+  P.dw = dw; P.ld_n = ld; P.ld_k = 1; P.k0 = 0; P.n_valid = n_valid; P.bias = nullptr; P.cta0 = 0; P.ncta = 1;
+  return fnerf::launch_wgrad_tc(B, (cudaStream_t)stream);
 }

@@ -18,6 +18,9 @@ from .model import NerfModel
 _T = torch.Tensor
 _tvals_cache: Dict[tuple, torch.Tensor] = {}
 _profile_events = None
+# tapes of the most recent save_tape forward, handed from the op implementation to its setup_context (same
+# thread, back to back).  They are NOT op outputs: autograd would materialise multi-GB zero "gradients" for them.
+_pending_tapes = None
 
 
 def set_profile_events(events) -> None:
@@ -40,7 +43,7 @@ def _linspace01(n: int, device) -> torch.Tensor:
 
 
 def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c, cond_proj_f,
-                 cond_index, n_importance, white_bkgd, lindisp, precision) -> List[_T]:
+                 cond_index, n_importance, white_bkgd, lindisp, precision, save_tape=False) -> List[_T]:
     lib = _lib.load()
     dev = rays_o.device
     R, Nc, Nf = rays_o.shape[0], t_vals.numel(), int(n_importance)
@@ -76,6 +79,16 @@ def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat,
         a.z_f, a.raw_f = z_f.data_ptr(), raw_f.data_ptr()
     a.weights_f = None
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    global _pending_tapes
+    _pending_tapes = None
+    tape_c = tape_f = None
+    if save_tape:                        # training forward: activations taped for the tensor-core backward
+        tape_c = torch.empty(max(ops.mlp_tape_bytes(R, Nc), 16), dtype=torch.uint8, device=dev)
+        a.tape_coarse, a.tape_coarse_bytes = tape_c.data_ptr(), tape_c.numel()
+        if Nf > 0:
+            tape_f = torch.empty(max(ops.mlp_tape_bytes(R, S), 16), dtype=torch.uint8, device=dev)
+            a.tape_fine, a.tape_fine_bytes = tape_f.data_ptr(), tape_f.numel()
+        _pending_tapes = (tape_c, tape_f)
     if _profile_events is not None:      # (coarse_start, coarse_stop, fine_start, fine_stop) torch.cuda.Event
         a.ev_coarse_start, a.ev_coarse_stop, a.ev_fine_start, a.ev_fine_stop = [e.cuda_event for e in _profile_events]
     with torch.cuda.device(dev):
@@ -87,16 +100,16 @@ def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat,
 def render_rays_op(flat_c: _T, flat_f: _T, packed_c: _T, packed_f: _T, rays_o: _T, rays_d: _T, near: _T, far: _T,
                    t_vals: _T, u_strat: Optional[_T], u_fine: Optional[_T], cond_proj_c: Optional[_T],
                    cond_proj_f: Optional[_T], cond_index: Optional[_T], cond_rows: Optional[_T], n_importance: int,
-                   white_bkgd: bool, lindisp: bool, precision: int) -> List[_T]:
+                   white_bkgd: bool, lindisp: bool, precision: int, save_tape: bool) -> List[_T]:
     # flat_c / flat_f only anchor the autograd graph (and cond_rows only feeds the backward); the
     # forward kernels read the packed blobs and the hoisted projections.
     return _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c,
-                        cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision)
+                        cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision, save_tape)
 
 
 @render_rays_op.register_fake
 def _(flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c,
-      cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision):
+      cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision, save_tape):
     R, Nc, S = rays_o.shape[0], t_vals.numel(), t_vals.numel() + n_importance
     e = rays_o.new_empty
     zf, rf = (e(R, S), e(R, S, 4)) if n_importance > 0 else (e(0), e(0))
@@ -105,9 +118,11 @@ def _(flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_s
 
 def _setup_context(ctx, inputs, output):
     (flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, cond_proj_c,
-     cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision) = inputs
-    z_c, z_f, raw_c, raw_f = output[8], output[9], output[10], output[11]
+     cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision, save_tape) = inputs
+    global _pending_tapes
+    z_c, z_f, raw_c, raw_f = output[8:12]
     ctx.save_for_backward(packed_c, packed_f, rays_o, rays_d, z_c, z_f, raw_c, raw_f, cond_rows, cond_index)
+    ctx.tapes, _pending_tapes = (_pending_tapes if save_tape else None), None
     ctx.n_importance, ctx.white_bkgd, ctx.precision = n_importance, white_bkgd, precision
     ctx.n_c, ctx.n_f = flat_c.numel(), flat_f.numel()
 
@@ -116,13 +131,15 @@ def _backward(ctx, grads):
     """A.6 + MLP backward for the training loss (grads w.r.t. rgb/acc/depth maps; disp and z_std carry
     none in A.10).  Sample positions are detached (A.7)."""
     packed_c, packed_f, rays_o, rays_d, z_c, z_f, raw_c, raw_f, cond_rows, cidx = ctx.saved_tensors
+    tape_c, tape_f = ctx.tapes if ctx.tapes is not None else (None, None)
+    ctx.tapes = None
     g_rgb, _g_disp, g_acc, g_depth, g_rgb0, _g_disp0, g_acc0 = grads[:7]
     viewdirs, dnorm = ops.ray_setup(rays_d)
     R = rays_o.shape[0]
     dev = rays_o.device
     zeros3 = None
 
-    def grad_net(packed, z, raw, gr, gd, ga, n_params):
+    def grad_net(packed, z, raw, gr, gd, ga, n_params, tape):
         nonlocal zeros3
         if gr is None and gd is None and ga is None:
             return None
@@ -131,18 +148,21 @@ def _backward(ctx, grads):
             gr = zeros3
         g_raw = ops.composite_bwd(raw, z, dnorm, gr.contiguous(), gd, ga, white_bkgd=ctx.white_bkgd)
         flat_grad = torch.zeros(n_params, dtype=torch.float32, device=dev)
-        # same arithmetic as the forward that produced `raw` (bf16: ReLU masks come from the bf16 forward)
+        if tape is not None:     # the forward taped its activations: dgrad + wgrad straight from the tape
+            ops.mlp_bwd_tape(packed, g_raw, tape, flat_grad)
+            return flat_grad
+        # otherwise recompute, with the same arithmetic as the forward that produced `raw`
         ops.mlp_bwd(packed, rays_o, rays_d, viewdirs, z, g_raw, flat_grad, precision=_PRECISION_NAMES[ctx.precision],
                     cond_rows=cond_rows, cond_index=cidx)
         return flat_grad
 
     if ctx.n_importance > 0:
-        g_flat_f = grad_net(packed_f, z_f, raw_f, g_rgb, g_depth, g_acc, ctx.n_f)
-        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb0, None, g_acc0, ctx.n_c)
+        g_flat_f = grad_net(packed_f, z_f, raw_f, g_rgb, g_depth, g_acc, ctx.n_f, tape_f)
+        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb0, None, g_acc0, ctx.n_c, tape_c)
     else:
         g_flat_f = None
-        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb, g_depth, g_acc, ctx.n_c)
-    return (g_flat_c, g_flat_f) + (None,) * 17
+        g_flat_c = grad_net(packed_c, z_c, raw_c, g_rgb, g_depth, g_acc, ctx.n_c, tape_c)
+    return (g_flat_c, g_flat_f) + (None,) * 18
 
 
 render_rays_op.register_autograd(_backward, setup_context=_setup_context)
@@ -166,13 +186,16 @@ def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, ne
                 N_importance: int, cond: Optional[torch.Tensor] = None, *, view_id: Optional[torch.Tensor] = None,
                 u_strat: Optional[torch.Tensor] = None, u_fine: Optional[torch.Tensor] = None,
                 white_bkgd: bool = False, lindisp: bool = False, precision: str = "bf16",
-                return_taps: bool = False) -> Dict[str, torch.Tensor]:
+                return_taps: bool = False, save_tape: Optional[bool] = None) -> Dict[str, torch.Tensor]:
     """Volume-render a batch of rays (A.9).
 
     rays_o, rays_d: [R,3] CUDA fp32 (rays_d un-normalised).  near/far: floats or [R]/[R,1] tensors.
     cond: None | [256] | [R,256] | [V,256] with view_id[R] (A.8; requires a model built with cond=True).
     u_strat [R,N_samples] / u_fine [R,N_importance]: caller-supplied uniforms; None = deterministic
     (no jitter; u_fine = linspace(0,1,N_importance)).
+    save_tape: record the networks' activations during the forward so that backward() skips the recompute
+    (bf16, unconditioned; ~5.4 KB per sample of HBM until backward).  None = automatically, when gradients are
+    being recorded for the model's parameters.
     Returns rgb[R,3], disp, acc, depth, rgb0, disp0, acc0, z_std (+ taps z_c, z_f, raw_c, raw_f).
     """
     if not rays_o.is_cuda:
@@ -205,10 +228,15 @@ def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, ne
         cpf = ops.cond_project(model.fine.packed, cond)
     elif model.cond:
         raise ValueError("model expects cond")
+    can_tape = precision == "bf16" and cond is None
+    if save_tape is None:
+        save_tape = can_tape and torch.is_grad_enabled() and (model.coarse.flat.requires_grad or model.fine.flat.requires_grad)
+    elif save_tape and not can_tape:
+        raise ValueError("save_tape needs precision='bf16' and an unconditioned model")
     outs = render_rays_op(model.coarse.flat, model.fine.flat, model.coarse.packed, model.fine.packed, rays_o, rays_d,
                           near_t, far_t, t_vals, u_strat, u_fine if N_importance > 0 else None, cpc, cpf, cidx,
                           cond if cond is not None else None, int(N_importance), bool(white_bkgd), bool(lindisp),
-                          ops.PRECISIONS[precision])
+                          ops.PRECISIONS[precision], bool(save_tape))
     n = len(_OUT_NAMES) if return_taps else 8
     return {k: v for k, v in zip(_OUT_NAMES[:n], outs[:n])}
 

@@ -257,3 +257,43 @@ def test_trainer_bf16_tracks_fp32(F, cuda_device):
     assert traj["bf16"][-1] < traj["bf16"][0]
     for a, b in zip(traj["bf16"], traj["fp32"]):
         assert abs(a - b) <= 2e-3, traj
+
+
+def test_tape_forward_and_backward_match_recompute(F, cuda_device):
+    """fnerf_mlp_fwd_tape returns the same raw bits as fnerf_mlp_fwd(bf16); fnerf_mlp_bwd_tape on that tape
+    equals fnerf_mlp_bwd(bf16), which re-runs the forward internally (only the fp32 atomic order differs)."""
+    dev = cuda_device
+    R, S = 517, 37                                                   # 19129 samples: 149 full tiles + 57 rows
+    o, d, z, g_raw = (t.to(dev) for t in _bf16_case(35, R, S, dev))
+    net = F.NerfNetwork.random(6, dev)
+    vd, _ = F.ops.ray_setup(d)
+    raw_ref = F.ops.mlp_fwd(net.packed, o, d, vd, z, precision="bf16")
+    raw, tape = F.ops.mlp_fwd_tape(net.packed, o, d, vd, z)
+    assert torch.equal(raw, raw_ref)
+    a = torch.zeros(net.flat.numel(), device=dev)
+    b = torch.zeros_like(a)
+    F.ops.mlp_bwd_tape(net.packed, g_raw, tape, a)
+    F.ops.mlp_bwd(net.packed, o, d, vd, z, g_raw, b, precision="bf16")
+    assert torch.isfinite(a).all()
+    assert _rel_err(a, b) <= 1e-5
+
+
+def test_render_rays_tape_backward_equals_recompute(F, cuda_device):
+    """render_rays(save_tape=True).backward() == render_rays(save_tape=False).backward() (bf16)."""
+    dev = cuda_device
+    o, d = (t.to(dev) for t in O.pinhole_rays(20, 20))
+    R, Nc, Nf = o.shape[0], 32, 48
+    g = torch.Generator().manual_seed(5)
+    u_s, u_f = torch.rand(R, Nc, generator=g).to(dev), torch.rand(R, Nf, generator=g).to(dev)
+    tgt = torch.rand(R, 3, generator=g).to(dev)
+    grads = {}
+    for save in (True, False):
+        model = F.NerfModel.random(dev)
+        model.coarse.flat.requires_grad_(True)
+        model.fine.flat.requires_grad_(True)
+        out = F.render_rays(model, o, d, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f, save_tape=save)
+        (((out["rgb"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean()).backward()
+        grads[save] = (model.coarse.flat.grad.clone(), model.fine.flat.grad.clone(), out["rgb"].detach().clone())
+    assert torch.equal(grads[True][2], grads[False][2])
+    assert _rel_err(grads[True][0], grads[False][0]) <= 1e-5
+    assert _rel_err(grads[True][1], grads[False][1]) <= 1e-5
