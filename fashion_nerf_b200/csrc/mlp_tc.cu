@@ -46,7 +46,7 @@ constexpr uint32_t kOffW = kOffPed + kKBlockBytes;              // weight stages
 constexpr uint32_t kOffHeads = kOffW + kStages * kBigChunkBytes;  // fp32 head weights (aux from kAuxWAlpha on)
 constexpr int kHeadFloats = kAuxFloats - kAuxWAlpha;
 constexpr uint32_t kOffBar = kOffHeads + kHeadFloats * 4;
-constexpr uint32_t kNumBars = 2 * kStages + 4 + 1 + 2 + 1;     // + tape-store drain barrier (training forward)
+constexpr uint32_t kNumBars = 2 * kStages + 4 + 1 + 2;
 constexpr uint32_t kTcSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;  // + tmem ptr + alignment slack
 static_assert(kOffBar % 8 == 0, "barrier alignment");
 static_assert(kTcSmemBytes <= 227 * 1024, "shared memory budget");
@@ -93,12 +93,6 @@ struct TcParams {
   uint8_t* tape;        // kSave only: per tile kTapeFwdSlots K-block images (layout.h), the shared-memory bytes verbatim
   uint32_t* mask_tape;  // kSave only: per tile kMaskUnits x 128 ReLU bitmask words (layout.h)
 };
-
-// tape slot of the activation K-block that gated chunk c consumes (the output of the previous layer)
-__host__ __device__ constexpr int tape_slot_of_chunk(int c) {
-  const ChunkDesc d = chunk_desc(c);
-  return (d.layer == 10 ? kTapeSlotFeat : (d.layer == 9 ? kTapeSlotH + 28 : kTapeSlotH + 4 * (d.layer - 1))) + d.kb;
-}
 
 // two non-negative bf16 in one word -> bit 0 = (low half != 0), bit 16 = (high half != 0): adding 0x7FFF to a
 // non-negative bf16 (<= 0x7F80) sets bit 15 exactly when it is non-zero and never carries into the other half
@@ -154,6 +148,8 @@ __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __res
 }
 
 __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
+// named barrier of the two worker groups (8 warps) that share an activation K-block: pair 0 = groups 0, 1; pair 1 = groups 2, 3
+__device__ __forceinline__ void pair_bar_sync(uint32_t pair) { asm volatile("bar.sync %0, 256;" ::"r"(2u + pair) : "memory"); }
 
 template <bool kSave>
 __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
@@ -166,7 +162,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   auto bar_act = [&](int kb) { return bar0 + 8u * (2 * kStages + kb); };
   const uint32_t bar_pe = bar0 + 8u * (2 * kStages + 4);
   auto bar_acc = [&](int a) { return bar0 + 8u * (2 * kStages + 5 + a); };
-  const uint32_t bar_st = bar0 + 8u * (2 * kStages + 7);            // kSave: tape stores no longer read the activation tile
   const uint32_t tmem_slot = bar0 + 8u * kNumBars;
   float* heads_s = reinterpret_cast<float*>(base_ptr + kOffHeads);   // index with (kAux* - kAuxWAlpha)
 
@@ -183,7 +178,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     mbar_init(bar_pe, 256);                                       // encoding groups 0 and 1
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
-    mbar_init(bar_st, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -227,12 +221,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     {
       constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256);
       constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
-      // Training forward (kSave): lane 0 also streams every finished K-block image (encodings, H0..H7, feature,
-      // view-layer output) from shared memory to the tape with one 16 KB bulk store, issued where the
-      // issuer has just seen the image's act-ready barrier; after a layer's last MMA it drains the stores
-      // (wait_group.read) and signals bar_st, which the epilogue that overwrites the tile waits for.
       uint32_t wc = 0, act_cnt = 0, tile_cnt = 0;
-      [[maybe_unused]] uint32_t hv_cnt = 0;     // kSave: K-blocks 0/1 see one extra act-ready phase per tile (HV image)
       [[maybe_unused]] uint32_t tslot = 0;   // tracer: slots [0,256): (before waits, operands ready, issued) per chunk
       const uint64_t desc_act = umma_desc_sw128(base + kOffAct);
       const uint64_t desc_pe = umma_desc_sw128(base + kOffPe);
@@ -242,12 +231,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
       const uint32_t acc_addr[2] = {tmem_u, tmem_u + 256};
       for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride, ++tile_cnt) {
         mbar_wait(bar_pe, tile_cnt & 1u);
-        [[maybe_unused]] uint8_t* tape_tile = kSave ? P.tape + (size_t)tile * kTapeFwdSlots * kKBlockBytes : nullptr;
-        if (kSave && lane == 0) {
-          bulk_s2g(tape_tile + kTapeSlotPe * kKBlockBytes, base + kOffPe, kKBlockBytes);
-          bulk_s2g(tape_tile + kTapeSlotPed * kKBlockBytes, base + kOffPed, kKBlockBytes);
-          bulk_commit();
-        }
         bool w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full(wc % kStages), (wc / kStages) & 1u));
         bool a_ready = true;
 #pragma unroll
@@ -255,13 +238,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const MmaChunk op = mma_chunk(c);
           const uint32_t s = wc % kStages;
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
-          if (op.gated && !a_ready) mbar_wait(bar_act(op.kb), (act_cnt + ((kSave && op.kb < 2) ? hv_cnt : 0u)) & 1u);
-          if (kSave && op.gated) {
-            if (lane == 0) {
-              bulk_s2g(tape_tile + (size_t)tape_slot_of_chunk(c) * kKBlockBytes, base + kOffAct + (uint32_t)op.kb * kKBlockBytes, kKBlockBytes);
-              bulk_commit();
-            }
-          }
+          if (op.gated && !a_ready) mbar_wait(bar_act(op.kb), act_cnt & 1u);
           if (!w_ready) mbar_wait(bar_full(s), (wc / kStages) & 1u);
           tc_fence_after();
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
@@ -270,7 +247,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full((wc + 1) % kStages), ((wc + 1) / kStages) & 1u));
           if (c + 1 < kNumChunks) {
             const MmaChunk nx = mma_chunk(c + 1);
-            a_ready = nx.gated ? __all_sync(0xffffffffu, mbar_test_wait(bar_act(nx.kb), (act_next + ((kSave && nx.kb < 2) ? hv_cnt : 0u)) & 1u)) : true;
+            a_ready = nx.gated ? __all_sync(0xffffffffu, mbar_test_wait(bar_act(nx.kb), act_next & 1u)) : true;
           } else {
             a_ready = true;
           }
@@ -290,28 +267,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
             if (op.commit_acc) umma_commit(bar_acc(op.acc));
           }
           __syncwarp();
-          if (kSave && op.commit_acc && chunk_desc(c).layer != 0) {   // this layer read the activation tile: drain its stores
-            if (lane == 0) { bulk_wait_read<0>(); mbar_arrive(bar_st); }
-            __syncwarp();
-          }
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
           act_cnt = act_next;
           ++wc;
         }
-        if (kSave) {                 // view-layer output image (K-blocks 0, 1 of the activation tile)
-          mbar_wait(bar_act(0), (act_cnt + hv_cnt) & 1u);
-          mbar_wait(bar_act(1), (act_cnt + hv_cnt) & 1u);
-          if (lane == 0) {
-            bulk_s2g(tape_tile + (size_t)kTapeSlotHv * kKBlockBytes, base + kOffAct, 2 * kKBlockBytes);
-            bulk_commit();
-            bulk_wait_read<0>();
-            mbar_arrive(bar_st);
-          }
-          __syncwarp();
-          ++hv_cnt;
-        }
       }
-      if (kSave && lane == 0) bulk_wait_all<0>();
     }
   } else {
     // ================================ workers: encodings + epilogues ===============================
@@ -320,9 +280,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     const uint32_t row = q * 32u + (uint32_t)lane;
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     uint32_t acc_cnt[2] = {0u, 0u};
-    [[maybe_unused]] uint32_t wtile_n = 0;                         // tiles this CTA has finished
     [[maybe_unused]] uint32_t wtile = 0, wslot = 256 + grp * 64;   // tracer: 64 slots per group from 256
-    [[maybe_unused]] uint32_t st_cnt = 0;                          // kSave: bar_st phases consumed
     const uint32_t act_row = base + kOffAct + row * 128u;
     uint8_t* ped_row_ptr = base_ptr + kOffPed + row * 128u;
     for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride) {
@@ -330,6 +288,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
       const int64_t gc = g < P.M ? g : P.M - 1;
       const int64_t ray = gc / P.S;
       [[maybe_unused]] uint32_t* mask_row = kSave ? P.mask_tape + (size_t)tile * (kMaskUnits * 128) + row : nullptr;
+      [[maybe_unused]] uint8_t* tape_tile = kSave ? P.tape + (size_t)tile * kTapeFwdSlots * kKBlockBytes : nullptr;
       // ---- positional encodings (A.3): sincos once, then double-angle recurrence per octave -----
       if (grp == 0) {
         const float zv = P.z[gc];
@@ -356,6 +315,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const uint4 pk = make_uint4(pack_bf16(f[c16 * 8 + 0], f[c16 * 8 + 1]), pack_bf16(f[c16 * 8 + 2], f[c16 * 8 + 3]),
                                       pack_bf16(f[c16 * 8 + 4], f[c16 * 8 + 5]), pack_bf16(f[c16 * 8 + 6], f[c16 * 8 + 7]));
           st_shared_v4(pe_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
+          if (kSave) *reinterpret_cast<uint4*>(tape_tile + kTapeSlotPe * kKBlockBytes + row * 128u + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_pe);
@@ -383,11 +343,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         const uint32_t ped_row = base + kOffPed + row * 128u;
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
-          // columns 32..63 of the tile are never multiplied by the forward (and hold the rgb partials at the end
-          // of a tile); the taped image carries them along, wgrad only writes out the first 27 columns
+          // columns 32..63 of the tile are never multiplied by the forward, and wgrad writes out only the first 27
+          // columns of its product with the taped image, so the upper half of the image stays undefined
           const uint4 pk = make_uint4(pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
                                       pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
           st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
+          if (kSave) *reinterpret_cast<uint4*>(tape_tile + kTapeSlotPed * kKBlockBytes + row * 128u + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
         }
         fence_proxy_async_smem();
         mbar_arrive(bar_pe);
@@ -408,10 +369,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         FN_TRACE(wtile == 2 && row == 0, wslot++);
         ++acc_cnt[a];
         tc_fence_after();
-        if (kSave && (step > 0 || wtile_n > 0)) {      // the tape stores of the tile's previous content have drained
-          mbar_wait(bar_st, st_cnt & 1u);
-          ++st_cnt;
-        }
         const uint32_t tacc = tmem_row + (uint32_t)a * 256u;
 #pragma unroll 1
         for (int round = 0; round < 2; ++round) {
@@ -420,6 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const uint32_t col0 = unit * 32u;
           const uint32_t dst = act_row + kb * kKBlockBytes;
           uint32_t* sv = kSave ? mask_row + (step * 8 + (int)unit) * 128 : nullptr;   // ReLU bitmask word (steps 0..7)
+          if (kSave) pair_bar_sync(grp >> 1);          // the pair's read-back of this K-block's previous image is done
           if (step == 8)
             epilogue_unit<false, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma, sv);
           else if (step == 7)
@@ -434,6 +392,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_act(kb));
+          if (kSave) {
+            // Training tape: the 16 KB image of K-block kb is complete once the two groups that share it have
+            // stored their halves.  Those 8 warps then copy it to the tape LINEARLY (2 KB per warp, 512
+            // contiguous bytes per instruction) -- a row-per-thread store of the same bytes touches 32 lines per
+            // instruction.  The same 8 warps overwrite this K-block at the next step, after the pair barrier
+            // above their stores, so the read-back never races a writer.
+            pair_bar_sync(grp >> 1);
+            const uint32_t off = (((grp & 1u) * 4u + q) << 11) + ((uint32_t)lane << 4);
+            const uint32_t src = base + kOffAct + kb * kKBlockBytes + off;
+            uint8_t* dstg = tape_tile + (size_t)(kTapeSlotH + 4 * step + (int)kb) * kKBlockBytes + off;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dstg + i * 512) = ld_shared_v4(src + i * 512);
+          }
           FN_TRACE(wtile == 2 && row == 0, wslot++);
         }
       }
@@ -455,9 +426,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           c1 = fmaf(h, wrgb[kWV + col], c1);
           c2 = fmaf(h, wrgb[2 * kWV + col], c2);
         }
-        if (kSave) {             // HV image -> K-blocks 0, 1 of the (now idle) activation tile; this group's 32 columns = 4 chunks
-          mbar_wait(bar_st, st_cnt & 1u);     // feature image stores have drained
-          ++st_cnt;
+        if (kSave) {             // HV image: 2 K-blocks of 64 columns; this group's 32 columns = 4 chunks of its row
+          uint8_t* hv_row = tape_tile + (size_t)(kTapeSlotHv + (int)(grp >> 1)) * kKBlockBytes + row * 128u;
           uint32_t mask = 0u;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -467,12 +437,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
                                         pack_bf16_relu(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])));
             mask |= relu_bits(pk.x) << (4 * c) | relu_bits(pk.y) << (4 * c + 1) | relu_bits(pk.z) << (4 * c + 2) | relu_bits(pk.w) << (4 * c + 3);
             const uint32_t c16 = (grp & 1u) * 4u + (uint32_t)c;
-            st_shared_v4(act_row + (grp >> 1) * kKBlockBytes + ((c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
+            *reinterpret_cast<uint4*>(hv_row + ((c16 ^ (row & 7u)) << 4)) = pk;
           }
           mask_row[(kMaskUnitHv + (int)grp) * 128] = mask;
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_act((int)(grp >> 1)));
         }
         tc_fence_before();
         // partials of groups 1..3 park in the unused upper half (logical chunks 5..7) of this row of
@@ -492,7 +459,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         }
       }
       ++wtile;
-      ++wtile_n;
     }
   }
 
