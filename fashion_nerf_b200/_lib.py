@@ -65,8 +65,8 @@ SIGNATURES = {
     "fnerf_mlp_fwd_tape": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "fnerf_mlp_bwd_tape_workspace_bytes": (c_int64, [c_int64, c_int64]),
-    "fnerf_mlp_bwd_tape": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
-                                   c_int64, c_void_p]),
+    "fnerf_mlp_bwd_tape": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                   c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "fnerf_composite_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "fnerf_composite_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -165,26 +165,30 @@ int fnerf_mlp_fwd_tape(const void* packed, int cond, const float* rays_o, const 
                        void* tape, int64_t tape_bytes, int64_t R, int64_t S, fnerf_stream_t stream) {
   int rc = validate_mlp("mlp_fwd_tape", FNERF_PRECISION_BF16, packed, cond, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, raw, R, S);
   if (rc != 0 || R == 0) return rc;
-  FN_REQUIRE(!cond, FNERF_ERR_ARG, "mlp_fwd_tape: conditioned networks train through fnerf_mlp_bwd (fp32 chain)");
   FN_REQUIRE(tape != nullptr, FNERF_ERR_NULL, "mlp_fwd_tape: null tape");
   FN_REQUIRE(FN_ALIGNED16(tape), FNERF_ERR_ALIGN, "mlp_fwd_tape: tape must be 16-byte aligned");
   FN_REQUIRE(tape_bytes >= mlp_tape_bytes(R * S), FNERF_ERR_WORKSPACE, "mlp_fwd_tape: tape too small");
-  MlpArgs a{packed, 0, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, raw, R, S};
+  MlpArgs a{packed, cond ? 1 : 0, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, raw, R, S};
   return launch_mlp_fwd_tape(a, tape, (cudaStream_t)stream);
 }
 
 int fnerf_mlp_bwd_tape(const void* packed, int cond, const float* g_raw, const void* tape, int64_t tape_bytes,
-                       float* flat_grad, void* workspace, int64_t workspace_bytes, int64_t R, int64_t S,
-                       fnerf_stream_t stream) {
+                       const float* cond_rows, const int32_t* cond_index, int64_t C, float* flat_grad, void* workspace,
+                       int64_t workspace_bytes, int64_t R, int64_t S, fnerf_stream_t stream) {
   FN_REQUIRE(R >= 0 && S >= 1, FNERF_ERR_SIZE, "mlp_bwd_tape: bad R=%lld S=%lld", (long long)R, (long long)S);
   if (R == 0) return 0;
-  FN_REQUIRE(!cond, FNERF_ERR_ARG, "mlp_bwd_tape: conditioned networks train through fnerf_mlp_bwd (fp32 chain)");
   FN_REQUIRE(packed && g_raw && tape && flat_grad && workspace, FNERF_ERR_NULL, "mlp_bwd_tape: null pointer");
+  if (cond) {
+    FN_REQUIRE(cond_rows != nullptr && C >= 1, FNERF_ERR_NULL, "mlp_bwd_tape: conditioned network needs the raw codes cond_rows[C,256]");
+    FN_REQUIRE(FN_ALIGNED16(cond_rows), FNERF_ERR_ALIGN, "mlp_bwd_tape: cond_rows must be 16-byte aligned");
+    FN_REQUIRE(cond_index != nullptr || C == 1 || C == R, FNERF_ERR_SIZE, "mlp_bwd_tape: C must be 1 or R without cond_index");
+  }
   FN_REQUIRE(FN_ALIGNED16(packed) && FN_ALIGNED16(g_raw) && FN_ALIGNED16(tape) && FN_ALIGNED16(workspace), FNERF_ERR_ALIGN,
              "mlp_bwd_tape: packed / g_raw / tape / workspace must be 16-byte aligned");
   FN_REQUIRE(tape_bytes >= mlp_tape_bytes(R * S), FNERF_ERR_WORKSPACE, "mlp_bwd_tape: tape too small");
   FN_REQUIRE(workspace_bytes >= mlp_bwd_from_tape_workspace_bytes(R * S), FNERF_ERR_WORKSPACE, "mlp_bwd_tape: workspace too small");
-  return launch_mlp_bwd_from_tape(packed, 0, g_raw, tape, flat_grad, workspace, R * S, (cudaStream_t)stream);
+  return launch_mlp_bwd_from_tape(packed, cond ? 1 : 0, g_raw, tape, cond_rows, cond_index, C, S, flat_grad, workspace, R * S,
+                                  (cudaStream_t)stream);
 }
 
 int fnerf_composite_fwd(const float* raw, const float* z, const float* dnorm, const float* raw_noise,
@@ -225,8 +229,8 @@ int fnerf_render_rays(const fnerf_render_args* a, fnerf_stream_t stream) {
              "render_rays: null output");
   FN_REQUIRE(Nf == 0 || (a->packed_fine && a->u_fine), FNERF_ERR_NULL, "render_rays: fine pass needs packed_fine and u_fine");
   FN_REQUIRE(a->workspace != nullptr, FNERF_ERR_NULL, "render_rays: null workspace");
-  FN_REQUIRE((!a->tape_coarse && !a->tape_fine) || (a->precision == FNERF_PRECISION_BF16 && !a->cond), FNERF_ERR_ARG,
-             "render_rays: training tapes need the bf16 path and an unconditioned network");
+  FN_REQUIRE((!a->tape_coarse && !a->tape_fine) || a->precision == FNERF_PRECISION_BF16, FNERF_ERR_ARG,
+             "render_rays: training tapes need the bf16 path");
   FN_REQUIRE(FN_ALIGNED16(a->workspace), FNERF_ERR_ALIGN, "render_rays: workspace must be 16-byte aligned");
   const RenderWorkspace L = render_layout(R, Nc, Nf);
   FN_REQUIRE(a->workspace_bytes >= L.total, FNERF_ERR_WORKSPACE, "render_rays: workspace %lld < %lld",

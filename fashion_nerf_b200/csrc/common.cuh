@@ -68,8 +68,9 @@ int64_t mlp_bwd_tc_workspace_bytes(int64_t M);
 int64_t mlp_tape_bytes(int64_t M);                       // forward tape of one bf16 network query
 int64_t mlp_bwd_from_tape_workspace_bytes(int64_t M);
 int launch_mlp_fwd_tape(const MlpArgs& a, void* tape, cudaStream_t s);
-int launch_mlp_bwd_from_tape(const void* packed, int cond, const float* g_raw, const void* tape, float* flat_grad, void* ws,
-                             int64_t M, cudaStream_t s);
+int launch_mlp_bwd_from_tape(const void* packed, int cond, const float* g_raw, const void* tape, const float* cond_rows,
+                             const int32_t* cond_index, int64_t C, int64_t S, float* flat_grad, void* ws, int64_t M,
+                             cudaStream_t s);
 int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws, int64_t ws_bytes, cudaStream_t s);
 int launch_mlp_bwd_fp32(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws,
                         int64_t ws_bytes, cudaStream_t s);

@@ -238,7 +238,27 @@ int64_t mlp_tape_bytes(int64_t M) {
   const int64_t ntiles = (M + 127) / 128;
   return ntiles * ((int64_t)kTapeFwdSlots * 16384 + kMaskTileBytes);
 }
-int64_t mlp_bwd_from_tape_workspace_bytes(int64_t M) { return (M + 127) / 128 * (int64_t)kTapeBwdSlots * 16384; }
+// backward tape + (conditioned networks) the per-sample garment codes as 4 K-block images per tile
+int64_t mlp_bwd_from_tape_workspace_bytes(int64_t M) { return (M + 127) / 128 * (int64_t)(kTapeBwdSlots + 4) * 16384; }
+
+// A.8 backward: the code block of W5 sees, for every sample, the code of its ray.  Written once per backward as
+// bf16 K-block images (same layout as the activation tape) so that dW5[:, 63:319] is one more wgrad product.
+__global__ void __launch_bounds__(256) k_tape_codes(const float* __restrict__ cond_rows, const int32_t* __restrict__ cond_index,
+                                                    int64_t C, int64_t M, int S, uint8_t* __restrict__ code_tape) {
+  const int64_t tile = blockIdx.x;
+  uint8_t* timg = code_tape + (size_t)tile * 4 * 16384;
+  for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {       // (row, 16-byte chunk of the 256 columns)
+    const uint32_t r = (uint32_t)e >> 5, ch = (uint32_t)e & 31u;    // ch: K-block ch / 8, chunk ch % 8
+    int64_t g = tile * 128 + r;
+    if (g >= M) g = M - 1;
+    const int64_t ray = g / S;
+    const int64_t crow = cond_index ? (int64_t)cond_index[ray] : (C == 1 ? 0 : ray);
+    const float4* src = reinterpret_cast<const float4*>(cond_rows + crow * kCond + ch * 8);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    *reinterpret_cast<uint4*>(timg + (size_t)(ch >> 3) * 16384 + r * 128u + (((ch & 7u) ^ (r & 7u)) << 4)) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+}
 // recomputing backward: forward tape | backward tape | raw scratch
 int64_t mlp_bwd_tc_workspace_bytes(int64_t M) {
   return mlp_tape_bytes(M) + mlp_bwd_from_tape_workspace_bytes(M) + (M + 127) / 128 * 128 * 16 + 4096;
@@ -252,15 +272,21 @@ int launch_mlp_fwd_tape(const MlpArgs& a, void* tape, cudaStream_t s) {
 
 // bf16 tensor-core backward of one network query from its forward tape: dgrad chain, then every
 // weight-gradient product (which also sums the bias gradients) and the two head products in one grouped
-// launch.  flat_grad += dL/dparams.  (Unconditioned networks; the conditioned variant uses the fp32 path.)
-int launch_mlp_bwd_from_tape(const void* packed, int cond, const float* g_raw, const void* tape, float* flat_grad, void* ws,
-                             int64_t M, cudaStream_t s) {
+// launch.  flat_grad += dL/dparams.  Conditioned networks (A.8) add the product with the per-sample codes.
+int launch_mlp_bwd_from_tape(const void* packed, int cond, const float* g_raw, const void* tape, const float* cond_rows,
+                             const int32_t* cond_index, int64_t C, int64_t S, float* flat_grad, void* ws, int64_t M,
+                             cudaStream_t s) {
   if (M == 0) return 0;
   const int64_t ntiles = (M + 127) / 128;
   const uint8_t* fwd_tape = reinterpret_cast<const uint8_t*>(tape);
   const uint32_t* mask_tape = reinterpret_cast<const uint32_t*>(fwd_tape + ntiles * (int64_t)kTapeFwdSlots * 16384);
   uint8_t* bwd_tape = reinterpret_cast<uint8_t*>(ws);
+  uint8_t* code_tape = bwd_tape + ntiles * (int64_t)kTapeBwdSlots * 16384;
   int rc;
+  if (cond) {
+    k_tape_codes<<<(unsigned)ntiles, 256, 0, s>>>(cond_rows, cond_index, C, M, (int)S, code_tape);
+    if ((rc = check_launch("tape_codes"))) return rc;
+  }
   if ((rc = launch_mlp_dgrad_tc(packed, cond, g_raw, mask_tape, bwd_tape, flat_grad, M, s))) return rc;
 
   const int64_t fstride = (int64_t)kTapeFwdSlots * 16384, bstride = (int64_t)kTapeBwdSlots * 16384;
@@ -281,12 +307,13 @@ int launch_mlp_bwd_from_tape(const void* packed, int cond, const float* g_raw, c
   auto gw = [&](int l) { return flat_grad + flat_weight_offset(l, cond); };
   auto gb = [&](int l) { return flat_grad + flat_bias_offset(l, cond); };
   auto zslot = [&](int l) { return kTapeBwdSlotZ + 4 * (7 - l); };
-  const int in5 = kPE + kW;
+  const int in5 = kPE + (cond ? kCond : 0) + kW;
   if ((rc = wz(zslot(0), 4, kTapeSlotPe, 1, gw(0), kPE, kPE, gb(0)))) return rc;
   for (int l = 1; l <= 7; ++l) {
     if (l == 5) {
       if ((rc = wz(zslot(5), 4, kTapeSlotPe, 1, gw(5), in5, kPE, nullptr))) return rc;
-      if ((rc = wz(zslot(5), 4, kTapeSlotH + 4 * 4, 4, gw(5) + kPE, in5, kW, gb(5)))) return rc;
+      if (cond && (rc = wg(bwd_tape, bstride, zslot(5), 4, code_tape, 4 * 16384, 0, 4, gw(5) + kPE, in5, 1, 0, kCond, nullptr))) return rc;
+      if ((rc = wz(zslot(5), 4, kTapeSlotH + 4 * 4, 4, gw(5) + (in5 - kW), in5, kW, gb(5)))) return rc;
     } else {
       if ((rc = wz(zslot(l), 4, kTapeSlotH + 4 * (l - 1), 4, gw(l), kW, kW, gb(l)))) return rc;
     }
@@ -312,7 +339,7 @@ int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, vo
   fa.raw = reinterpret_cast<float*>(bwd_ws + mlp_bwd_from_tape_workspace_bytes(M));
   int rc;
   if ((rc = launch_mlp_fwd_tape(fa, tape, s))) return rc;
-  return launch_mlp_bwd_from_tape(a.packed, 0, g_raw, tape, flat_grad, bwd_ws, M, s);
+  return launch_mlp_bwd_from_tape(a.packed, 0, g_raw, tape, nullptr, nullptr, 0, a.S, flat_grad, bwd_ws, M, s);
 }
 
 }  // namespace fnerf

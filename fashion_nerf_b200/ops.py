@@ -161,31 +161,43 @@ def mlp_tape_bytes(R: int, S: int) -> int:
     return int(_lib.load().fnerf_mlp_tape_bytes(R, S))
 
 
-def mlp_fwd_tape(packed: torch.Tensor, rays_o, rays_d, viewdirs, z):
-    """Training forward (bf16, unconditioned): returns (raw[R,S,4], tape) -- the tape is an opaque uint8 tensor
-    for mlp_bwd_tape."""
+def mlp_fwd_tape(packed: torch.Tensor, rays_o, rays_d, viewdirs, z, *, cond_proj=None, cond_index=None):
+    """Training forward (bf16): returns (raw[R,S,4], tape) -- the tape is an opaque uint8 tensor for mlp_bwd_tape."""
     rays_o, rays_d, viewdirs, z = (_f32(rays_o, "rays_o"), _f32(rays_d, "rays_d"), _f32(viewdirs, "viewdirs"),
                                    _f32(z, "z"))
     R, S = z.shape
     raw = torch.empty(R, S, 4, dtype=torch.float32, device=z.device)
     tape = torch.empty(max(mlp_tape_bytes(R, S), 16), dtype=torch.uint8, device=z.device)
+    has_cond = cond_proj is not None
+    C = cond_proj.shape[0] if has_cond else 0
+    if cond_index is not None:
+        cond_index = cond_index.to(torch.int32).contiguous()
     with torch.cuda.device(z.device):
-        check(_lib.load().fnerf_mlp_fwd_tape(packed.data_ptr(), 0, rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(),
-                                             z.data_ptr(), None, None, 0, raw.data_ptr(), tape.data_ptr(), tape.numel(),
-                                             R, S, _stream()), "mlp_fwd_tape")
+        check(_lib.load().fnerf_mlp_fwd_tape(packed.data_ptr(), int(has_cond), rays_o.data_ptr(), rays_d.data_ptr(),
+                                             viewdirs.data_ptr(), z.data_ptr(), _ptr(cond_proj), _ptr(cond_index), C,
+                                             raw.data_ptr(), tape.data_ptr(), tape.numel(), R, S, _stream()), "mlp_fwd_tape")
     return raw, tape
 
 
-def mlp_bwd_tape(packed: torch.Tensor, g_raw: torch.Tensor, tape: torch.Tensor, flat_grad: torch.Tensor) -> torch.Tensor:
-    """flat_grad += dL/dparams from the tape of mlp_fwd_tape / render_rays(save_tape=True) and g_raw[R,S,4]."""
+def mlp_bwd_tape(packed: torch.Tensor, g_raw: torch.Tensor, tape: torch.Tensor, flat_grad: torch.Tensor, *,
+                 cond_rows=None, cond_index=None) -> torch.Tensor:
+    """flat_grad += dL/dparams from the tape of mlp_fwd_tape / render_rays(save_tape=True) and g_raw[R,S,4].
+    cond_rows: RAW codes [C,256] of a conditioned network."""
     g_raw = _f32(g_raw, "g_raw")
     R, S = g_raw.shape[:2]
+    has_cond = cond_rows is not None
+    if has_cond:
+        cond_rows = _f32(cond_rows, "cond_rows").reshape(-1, 256)
+    C = cond_rows.shape[0] if has_cond else 0
+    if cond_index is not None:
+        cond_index = cond_index.to(torch.int32).contiguous()
     lib = _lib.load()
     ws_bytes = int(lib.fnerf_mlp_bwd_tape_workspace_bytes(R, S))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=g_raw.device)
     with torch.cuda.device(g_raw.device):
-        check(lib.fnerf_mlp_bwd_tape(packed.data_ptr(), 0, g_raw.data_ptr(), tape.data_ptr(), tape.numel(),
-                                     flat_grad.data_ptr(), ws.data_ptr(), ws.numel(), R, S, _stream()), "mlp_bwd_tape")
+        check(lib.fnerf_mlp_bwd_tape(packed.data_ptr(), int(has_cond), g_raw.data_ptr(), tape.data_ptr(), tape.numel(),
+                                     _ptr(cond_rows), _ptr(cond_index), C, flat_grad.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     R, S, _stream()), "mlp_bwd_tape")
     return flat_grad
 
 

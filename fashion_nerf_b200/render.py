@@ -149,7 +149,7 @@ def _backward(ctx, grads):
         g_raw = ops.composite_bwd(raw, z, dnorm, gr.contiguous(), gd, ga, white_bkgd=ctx.white_bkgd)
         flat_grad = torch.zeros(n_params, dtype=torch.float32, device=dev)
         if tape is not None:     # the forward taped its activations: dgrad + wgrad straight from the tape
-            ops.mlp_bwd_tape(packed, g_raw, tape, flat_grad)
+            ops.mlp_bwd_tape(packed, g_raw, tape, flat_grad, cond_rows=cond_rows, cond_index=cidx)
             return flat_grad
         # otherwise recompute, with the same arithmetic as the forward that produced `raw`
         ops.mlp_bwd(packed, rays_o, rays_d, viewdirs, z, g_raw, flat_grad, precision=_PRECISION_NAMES[ctx.precision],
@@ -194,7 +194,7 @@ def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, ne
     u_strat [R,N_samples] / u_fine [R,N_importance]: caller-supplied uniforms; None = deterministic
     (no jitter; u_fine = linspace(0,1,N_importance)).
     save_tape: record the networks' activations during the forward so that backward() skips the recompute
-    (bf16, unconditioned; ~5.4 KB per sample of HBM until backward).  None = automatically, when gradients are
+    (bf16 path; ~5.4 KB per sample of HBM until backward).  None = automatically, when gradients are
     being recorded for the model's parameters.
     Returns rgb[R,3], disp, acc, depth, rgb0, disp0, acc0, z_std (+ taps z_c, z_f, raw_c, raw_f).
     """
@@ -228,11 +228,11 @@ def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, ne
         cpf = ops.cond_project(model.fine.packed, cond)
     elif model.cond:
         raise ValueError("model expects cond")
-    can_tape = precision == "bf16" and cond is None
+    can_tape = precision == "bf16"
     if save_tape is None:
         save_tape = can_tape and torch.is_grad_enabled() and (model.coarse.flat.requires_grad or model.fine.flat.requires_grad)
     elif save_tape and not can_tape:
-        raise ValueError("save_tape needs precision='bf16' and an unconditioned model")
+        raise ValueError("save_tape needs precision='bf16'")
     outs = render_rays_op(model.coarse.flat, model.fine.flat, model.coarse.packed, model.fine.packed, rays_o, rays_d,
                           near_t, far_t, t_vals, u_strat, u_fine if N_importance > 0 else None, cpc, cpf, cidx,
                           cond if cond is not None else None, int(N_importance), bool(white_bkgd), bool(lindisp),

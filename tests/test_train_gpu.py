@@ -297,3 +297,69 @@ def test_render_rays_tape_backward_equals_recompute(F, cuda_device):
     assert torch.equal(grads[True][2], grads[False][2])
     assert _rel_err(grads[True][0], grads[False][0]) <= 1e-5
     assert _rel_err(grads[True][1], grads[False][1]) <= 1e-5
+
+
+@pytest.mark.parametrize("flip_free", [False, True])
+def test_cond_bf16_tape_backward(F, cuda_device, flip_free):
+    """Conditioned network (A.8) through the tape path: fnerf_mlp_fwd_tape with hoisted projections, then
+    fnerf_mlp_bwd_tape with the raw codes, vs autograd of the oracle MLP with bf16 rounding points.  The
+    flip-free variant (weights x0.1, biases +-1) pins the arithmetic to 1e-2; the random-init variant carries
+    the ReLU mask flips discussed above (0.12)."""
+    dev = cuda_device
+    R, S, V = 45, 29, 3
+    o, d, z, g_raw = _bf16_case(41, R, S, dev)
+    vd, _ = O.ray_setup(d)
+    g = torch.Generator().manual_seed(42)
+    p = O.init_params(7, cond=True)
+    codes = 0.25 * torch.randn(V, 256, generator=g)
+    vid = torch.randint(0, V, (R,), generator=g)
+    if flip_free:
+        for k in p:
+            if k.endswith("weight") and not k.startswith(("alpha", "rgb")):
+                p[k] = 0.1 * p[k]
+            if k.endswith("bias") and k.startswith(("pts", "views")):
+                p[k] = (torch.randint(0, 2, p[k].shape, generator=g) * 2 - 1).float()
+    pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    raw_ref = O.run_network(pr, pts, vd, codes[vid], bf16=True)
+    (raw_ref * g_raw).sum().backward()
+    net = F.NerfNetwork.from_state_dict(p, dev, cond=True)
+    proj = F.ops.cond_project(net.packed, codes.to(dev))
+    raw, tape = F.ops.mlp_fwd_tape(net.packed, o.to(dev), d.to(dev), vd.to(dev), z.to(dev), cond_proj=proj, cond_index=vid.to(dev))
+    assert torch.equal(raw, F.ops.mlp_fwd(net.packed, o.to(dev), d.to(dev), vd.to(dev), z.to(dev), precision="bf16",
+                                          cond_proj=proj, cond_index=vid.to(dev)))
+    flat_grad = torch.zeros(net.flat.numel(), device=dev)
+    F.ops.mlp_bwd_tape(net.packed, g_raw.to(dev), tape, flat_grad, cond_rows=codes.to(dev), cond_index=vid.to(dev))
+    got = F.unflatten(flat_grad.cpu(), True)
+    assert torch.isfinite(flat_grad).all()
+    tol = 1e-2 if flip_free else 0.12
+    for k in pr:
+        e = _rel_err(got[k], pr[k].grad)
+        assert e <= tol, (k, e)
+    # the code block of W5 (columns 63:319) on its own
+    w5, w5_ref = got["pts_linears.5.weight"], pr["pts_linears.5.weight"].grad
+    assert _rel_err(w5[:, 63:319], w5_ref[:, 63:319]) <= tol
+
+
+def test_trainer_cond_bf16_tracks_fp32(F, cuda_device):
+    """Conditioned model, bf16 forward + tape backward: 5 Adam steps stay within 2e-3 of the fp32 trajectory."""
+    from fashion_nerf_b200.train import Trainer
+    dev = cuda_device
+    o, d = (t.to(dev) for t in O.pinhole_rays(20, 20))
+    R, Nc, Nf, V = o.shape[0], 32, 32, 4
+    g = torch.Generator().manual_seed(8)
+    u_s, u_f = torch.rand(R, Nc, generator=g).to(dev), torch.rand(R, Nf, generator=g).to(dev)
+    tgt = torch.rand(R, 3, generator=g).to(dev)
+    codes = (0.25 * torch.randn(V, 256, generator=g)).to(dev)
+    vid = torch.randint(0, V, (R,), generator=g).to(dev)
+    traj = {}
+    for prec in ("fp32", "bf16"):
+        pc, pf = O.init_params(0, cond=True), O.init_params(1, cond=True)
+        for p in (pc, pf):
+            p["alpha_linear.bias"] += 0.1
+        model = F.NerfModel(F.NerfNetwork.from_state_dict(pc, dev, cond=True), F.NerfNetwork.from_state_dict(pf, dev, cond=True))
+        tr = Trainer(model)
+        traj[prec] = [tr.step(o, d, tgt, 2.0, 6.0, Nc, Nf, codes, view_id=vid, u_strat=u_s, u_fine=u_f, precision=prec)["loss"].item()
+                      for _ in range(5)]
+    for a, b in zip(traj["bf16"], traj["fp32"]):
+        assert abs(a - b) <= 2e-3, traj
