@@ -41,7 +41,7 @@ __global__ void k_pack_bf16_T(const float* __restrict__ flat, uint8_t* __restric
   const LayerDim d = layer_dim(cd.layer, cond);
   const float* W = flat + flat_weight_offset(cd.layer, cond);
   const int base = (cd.layer == 5) ? kPE + (cond ? kCond : 0) : 0;
-  for (int e = threadIdx.x; e < 256 * 64; e += blockDim.x) {
+  for (int e = blockIdx.y * 4096 + threadIdx.x; e < (blockIdx.y + 1) * 4096; e += blockDim.x) {   // grid.y = 4 quarters of the chunk
     const int k = e >> 6, j = e & 63;
     const int n = cd.kb * 64 + j;
     const float v = W[(int64_t)n * d.in + base + k];
@@ -64,7 +64,8 @@ __global__ void k_pack_aux(const float* __restrict__ flat, float* __restrict__ a
 }
 
 // Section C: layer j stored K-major: wt[k][n] = W[n][k]
-__global__ void k_pack_simt(const float* __restrict__ flat, float* __restrict__ secC, int cond, int j) {
+__global__ void k_pack_simt(const float* __restrict__ flat, float* __restrict__ secC, int cond) {
+  const int j = blockIdx.y;                      // one grid row per fp32 layer
   const int l = simt_layer_id(j);
   const LayerDim d = layer_dim(l, cond);
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,12 +109,13 @@ int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s) {
   const int64_t total = (int64_t)kBigChunks * 256 * 64 + (int64_t)kSmallChunks * 128 * 64;
   k_pack_bf16<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(flat, p, cond);
   k_pack_aux<<<(kAuxFloats + 255) / 256, 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecBOffset), cond);
+  int64_t nmax = 0;
   for (int j = 0; j < 10; ++j) {
     const LayerDim d = layer_dim(simt_layer_id(j), cond);
-    const int64_t n = (int64_t)d.out * d.in;
-    k_pack_simt<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecCOffset), cond, j);
+    if ((int64_t)d.out * d.in > nmax) nmax = (int64_t)d.out * d.in;
   }
-  k_pack_bf16_T<<<kNumChunksT, 256, 0, s>>>(flat, p + sec_e_offset(cond), cond);
+  k_pack_simt<<<dim3((unsigned)((nmax + 255) / 256), 10), 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecCOffset), cond);
+  k_pack_bf16_T<<<dim3(kNumChunksT, 4), 256, 0, s>>>(flat, p + sec_e_offset(cond), cond);
   return check_launch("pack_weights");
 }
 
@@ -121,6 +123,30 @@ int launch_unpack(const void* packed, float* flat, int cond, cudaStream_t s) {
   const int64_t n = flat_count(cond);
   k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(packed), flat, cond);
   return check_launch("unpack_weights");
+}
+
+// ------------------------------------------------------------------------------------------ A.10
+// Adam on a flat fp32 buffer (torch semantics: m, v updated first; step = lr / (1 - b1^t); denom = sqrt(v / (1 - b2^t)) + eps)
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       int64_t n, float b1, float b2, float one_minus_b1, float one_minus_b2, float step_size, float inv_bc2,
+                       float eps, float grad_scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = fmaf(one_minus_b1, gi, m[i] * b1);
+  const float vi = fmaf(one_minus_b2 * gi, gi, v[i] * b2);
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= step_size * mi / (sqrtf(vi * inv_bc2) + eps);
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int64_t t,
+                float grad_scale, cudaStream_t s) {
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, b1, b2, 1.0f - b1, 1.0f - b2, (float)(lr / bc1), (float)(1.0 / bc2),
+                                                       eps, grad_scale);
+  return check_launch("adam_step");
 }
 
 // ------------------------------------------------------------------------------------------ A.3

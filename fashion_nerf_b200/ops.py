@@ -157,6 +157,17 @@ def mlp_bwd(packed: torch.Tensor, rays_o, rays_d, viewdirs, z, g_raw: torch.Tens
     return flat_grad
 
 
+def adam_step(params: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int, *,
+              lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0) -> None:
+    """Fused in-place Adam step over flat fp32 CUDA buffers (A.10)."""
+    for t in (params, grad, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise _lib.FnerfError("adam_step needs contiguous CUDA float32 buffers")
+    with torch.cuda.device(params.device):
+        check(_lib.load().fnerf_adam_step(params.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                          params.numel(), lr, betas[0], betas[1], eps, step, grad_scale, _stream()), "adam_step")
+
+
 def mlp_tape_bytes(R: int, S: int) -> int:
     return int(_lib.load().fnerf_mlp_tape_bytes(R, S))
 
