@@ -37,7 +37,8 @@ def test_ray_setup_bit_exact(F, cuda_device):
 # ------------------------------------------------------------------------------------------ A.2
 @pytest.mark.parametrize("R,N,jitter,lindisp", [(4096, 64, True, False), (4096, 64, False, False),
                                                 (1001, 256, True, False), (333, 7, True, True),
-                                                (5, 1, True, False), (64, 64, False, True)])
+                                                (5, 1, True, False), (64, 64, False, True), (100, 32, True, True),
+                                                (77, 12, True, False), (300000, 64, True, False)])
 def test_stratified_bit_exact(F, cuda_device, R, N, jitter, lindisp):
     g = _gen(1)
     near = 1.5 + torch.rand(R, generator=g)
