@@ -16,7 +16,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid through ex2.approx + rcp-based division (~6 instructions instead of ~30): relative error ~3e-7, which
+// enters the maps linearly (weights sum to <= 1); the transmittance product keeps the exact expf
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
   float4 v;
