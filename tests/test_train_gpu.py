@@ -380,3 +380,32 @@ def test_fused_adam_matches_oracle(F, cuda_device):
         F.ops.adam_step(p_dev, grad.to(dev), m_dev, v_dev, t)
         assert (p_dev.cpu() - params["w"]).abs().max() <= 2e-6
     assert (m_dev.cpu() - state["m"]["w"]).abs().max() <= 1e-6 * state["m"]["w"].abs().max()
+
+
+def test_checkpoint_model_and_optimizer_round_trip(F, cuda_device, tmp_path):
+    """save_checkpoint -> load_model renders the same bits; restore_optimizer resumes training bit-for-bit."""
+    from fashion_nerf_b200.train import Trainer
+    dev = cuda_device
+    o, d = (t.to(dev) for t in O.pinhole_rays(16, 16))
+    R, Nc, Nf = o.shape[0], 16, 16
+    g = torch.Generator().manual_seed(11)
+    u_s, u_f = torch.rand(R, Nc, generator=g).to(dev), torch.rand(R, Nf, generator=g).to(dev)
+    tgt = torch.rand(R, 3, generator=g).to(dev)
+    model = F.NerfModel.random(dev)
+    tr = Trainer(model)
+    for _ in range(2):
+        tr.step(o, d, tgt, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f)
+    path = str(tmp_path / "ck.tar")
+    F.checkpoint.save_checkpoint(path, model, global_step=2, trainer=tr)
+    model2, ck = F.checkpoint.load_model(path, dev)
+    assert ck["global_step"] == 2
+    with torch.no_grad():
+        a = F.render_rays(model, o, d, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f)["rgb"]
+        b = F.render_rays(model2, o, d, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f)["rgb"]
+    assert torch.equal(a, b)
+    tr2 = Trainer(model2)
+    F.checkpoint.restore_optimizer(tr2, ck)
+    l1 = tr.step(o, d, tgt, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f, precision="fp32")["loss"]
+    l2 = tr2.step(o, d, tgt, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f, precision="fp32")["loss"]
+    assert torch.equal(l1, l2)
+    assert (model.fine.flat - model2.fine.flat).abs().max() <= 1e-6      # fp32 atomics order in wgrad
