@@ -237,6 +237,8 @@ def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, ne
                           near_t, far_t, t_vals, u_strat, u_fine if N_importance > 0 else None, cpc, cpf, cidx,
                           cond if cond is not None else None, int(N_importance), bool(white_bkgd), bool(lindisp),
                           ops.PRECISIONS[precision], bool(save_tape))
+    global _pending_tapes
+    _pending_tapes = None                # not claimed by an autograd node (no grad recorded): release the tapes now
     n = len(_OUT_NAMES) if return_taps else 8
     return {k: v for k, v in zip(_OUT_NAMES[:n], outs[:n])}
 

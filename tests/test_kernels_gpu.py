@@ -257,6 +257,33 @@ def test_error_codes_and_no_cpu_fallback(F, cuda_device):
         F.ops.ray_setup(torch.zeros(4, 3))                              # CPU tensor: rejected, not emulated
 
 
+def test_error_codes_training_entries(F, cuda_device):
+    """Argument validation of the ABI v2 training entries: negative codes before any launch."""
+    lib = F.load_library()
+    dev = cuda_device
+    net = F.NerfNetwork.random(0, dev)
+    R, S = 8, 16
+    o = torch.zeros(R, 3, device=dev); d = torch.ones(R, 3, device=dev); z = torch.ones(R, S, device=dev)
+    raw = torch.empty(R, S, 4, device=dev)
+    tape = torch.empty(F.ops.mlp_tape_bytes(R, S), dtype=torch.uint8, device=dev)
+    p = lambda t: t.data_ptr()
+    assert F.ops.mlp_tape_bytes(R, S) == 40 * 16384 + 68 * 128 * 4          # one 128-sample tile
+    # tape too small / null tape / misaligned tape
+    assert lib.fnerf_mlp_fwd_tape(p(net.packed), 0, p(o), p(d), p(d), p(z), None, None, 0, p(raw), p(tape), tape.numel() - 1, R, S, None) == -5
+    assert lib.fnerf_mlp_fwd_tape(p(net.packed), 0, p(o), p(d), p(d), p(z), None, None, 0, p(raw), None, tape.numel(), R, S, None) == -1
+    assert lib.fnerf_mlp_fwd_tape(p(net.packed), 0, p(o), p(d), p(d), p(z), None, None, 0, p(raw), p(tape) + 4, tape.numel(), R, S, None) == -3
+    g = torch.zeros(R, S, 4, device=dev); fg = torch.zeros(net.flat.numel(), device=dev)
+    ws = torch.empty(int(lib.fnerf_mlp_bwd_tape_workspace_bytes(R, S)), dtype=torch.uint8, device=dev)
+    assert lib.fnerf_mlp_bwd_tape(p(net.packed), 0, p(g), p(tape), tape.numel(), None, None, 0, p(fg), p(ws), ws.numel() - 1, R, S, None) == -5
+    assert lib.fnerf_mlp_bwd_tape(p(net.packed), 1, p(g), p(tape), tape.numel(), None, None, 0, p(fg), p(ws), ws.numel(), R, S, None) == -1   # cond without codes
+    assert lib.fnerf_mlp_bwd_tape(p(net.packed), 0, p(g), p(tape), tape.numel(), None, None, 0, p(fg), p(ws), ws.numel(), 0, S, None) == 0    # R == 0: no-op
+    assert lib.fnerf_adam_step(p(fg), p(fg), p(fg), p(fg), fg.numel(), 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, None) == -2                            # step must be >= 1
+    assert lib.fnerf_adam_step(None, p(fg), p(fg), p(fg), fg.numel(), 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
+    with pytest.raises(ValueError):
+        F.render_rays(F.NerfModel(net, None), o, d, 2.0, 6.0, 8, 0, precision="fp32", save_tape=True)
+    assert fg.abs().max() == 0                                              # nothing above touched the gradient buffer
+
+
 def test_importance_descending_coarse_depths(F, cuda_device):
     """near > far gives descending coarse depths: the rank-merge fast path must hand over to the
     generic sort, and odd sizes must still be bit-exact."""
