@@ -38,6 +38,10 @@ N_C, N_F = 64, 128
 NEAR, FAR = 2.0, 6.0
 FLOP_PER_SAMPLE = 1_186_816          # un-padded 593,408 MAC
 FLOP_PER_RAY = FLOP_PER_SAMPLE * (N_C + N_C + N_F)
+# dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass k_mlp_tc launch of THIS workload (640,000 rays x 192
+# samples) from one `ncu --set full` capture of `bench.py --steps 1 --warmup 3` (profiles/r1_bench_fine_launch_ncu_key_metrics.txt);
+# the algorithmic HBM bytes of that launch are 20 B/sample = 2,457,600,000
+NCU_FINE_LAUNCH_DRAM_BYTES = 538_791_424 + 1_917_652_000
 CPU_SAMPLE_RAYS = 4096
 WORKLOAD = ("single-B200 full-frame 800x800 render per GPU (BASELINE configs[1]); view r of N per rank, "
             "random-init 8x256 NeRF MLPs (seeds 0/1), L=10/4 PE")
@@ -265,7 +269,10 @@ def main():
         roofline = {"bound": "tensor", "kernel": "k_mlp_tc (fine pass, 192 samples/ray)" if use_bf16 else "k_mlp_fp32",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "peak_kind": f"sustained, {peaks['source']}",
-                    "traffic": None, "launch_ms": fine_ms, "coarse_launch_ms": coarse_ms,
+                    "traffic": NCU_FINE_LAUNCH_DRAM_BYTES if (use_bf16 and R == 640000) else None,
+                    "traffic_source": "profiles/r1_bench_fine_launch_ncu_key_metrics.txt (dram read + write of this launch, ncu --set full)",
+                    "algorithmic_hbm_bytes": R * (N_C + N_F) * 20,
+                    "launch_ms": fine_ms, "coarse_launch_ms": coarse_ms,
                     "kernel_share_of_step": (fine_ms + coarse_ms) / ms_step,
                     "step_tensor_frac": R * FLOP_PER_RAY / (ms_step * 1e-3) / 1e12 / peak}
         line = {
