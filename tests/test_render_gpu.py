@@ -219,3 +219,55 @@ def test_mlp_bf16_tile_tail_and_sizes(F, cuda_device):
         b = F.ops.mlp_fwd(net.packed, o, d, vd, z, precision="bf16")
         assert torch.isfinite(b).all()
         assert (a - b).abs().max() <= 2e-3, (R, S, (a - b).abs().max().item())
+
+
+def test_full_size_frame_properties(F, cuda_device):
+    """BASELINE configs[1] at its full size (800x800 = 640,000 rays, 64+128) through size-independent properties:
+    chunking invariance (bit-for-bit), sorted merged depths, weights / opacity bounds, finite maps."""
+    dev = cuda_device
+    model = F.NerfModel.random(dev)
+    o, d = F.pinhole_rays(800, 800, device=dev)
+    R = o.shape[0]
+    assert R == 640000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    u_s = torch.rand(R, 64, device=dev, generator=g)
+    u_f = torch.rand(R, 128, device=dev, generator=g)
+    a = F.render_image(model, o, d, 2.0, 6.0, 64, 128, chunk=1 << 16, u_strat=u_s, u_fine=u_f)
+    b = F.render_image(model, o, d, 2.0, 6.0, 64, 128, chunk=100_003, u_strat=u_s, u_fine=u_f)   # ragged chunks, tile tails
+    for k in a:
+        assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k      # bit patterns: disp may hold NaN
+        if k in ("disp", "disp0"):      # A.5: disp = 1 / max(1e-10, depth / acc) is NaN exactly where acc == 0 (0 / 0)
+            acc = a["acc" if k == "disp" else "acc0"]
+            assert torch.equal(torch.isnan(a[k]), acc == 0), k
+        else:
+            assert torch.isfinite(a[k]).all(), k
+    assert a["rgb"].min() >= 0 and a["rgb"].max() <= 1 + 1e-5
+    assert a["acc"].min() >= -1e-6 and a["acc"].max() <= 1 + 1e-5
+    assert (a["depth"] <= 6.0 * a["acc"] * 1.0001 + 1e-4).all()          # depth = sum w z <= far * sum w (|d| folded in z)
+    sl = slice(300_000, 320_000)
+    with torch.no_grad():
+        taps = F.render_rays(model, o[sl], d[sl], 2.0, 6.0, 64, 128, u_strat=u_s[sl], u_fine=u_f[sl], return_taps=True)
+    zf = taps["z_f"]
+    assert (zf[:, 1:] >= zf[:, :-1]).all()                               # merged depths sorted
+    assert zf.min() >= 2.0 - 1e-6 and zf.max() <= 6.0 + 1e-6
+    assert torch.equal(taps["rgb"], a["rgb"][sl])                        # a slice re-rendered alone: same bits
+
+
+def test_cfg4_shard_properties(F, cuda_device):
+    """BASELINE configs[3] sizes (256 coarse + 768 fine samples per ray) on a 32,400-ray slice of the 1920x1080 frame
+    (1/64 of it): sorted 1024-sample merges, opacity bounds, chunking invariance of the long-ray kernels."""
+    dev = cuda_device
+    model = F.NerfModel.random(dev)
+    o, d = F.pinhole_rays(1080, 1920, device=dev)
+    sl = slice(1_000_000, 1_032_400)
+    o, d = o[sl].contiguous(), d[sl].contiguous()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    u_s = torch.rand(o.shape[0], 256, device=dev, generator=g)
+    u_f = torch.rand(o.shape[0], 768, device=dev, generator=g)
+    with torch.no_grad():
+        full = F.render_rays(model, o, d, 2.0, 6.0, 256, 768, u_strat=u_s, u_fine=u_f, return_taps=True)
+        half = F.render_rays(model, o[:9001], d[:9001], 2.0, 6.0, 256, 768, u_strat=u_s[:9001], u_fine=u_f[:9001])
+    zf = full["z_f"]
+    assert zf.shape == (o.shape[0], 1024) and (zf[:, 1:] >= zf[:, :-1]).all()
+    assert torch.isfinite(full["rgb"]).all() and full["acc"].max() <= 1 + 1e-5 and full["acc"].min() >= -1e-6
+    assert torch.equal(half["rgb"], full["rgb"][:9001])
