@@ -28,6 +28,7 @@
 // Encoded samples and activations never touch HBM: per sample the kernel reads 4 B (z) and writes
 // 16 B (raw).  sigma (256->1) and rgb (128->3) are fp32 dot products inside the epilogues of layer 7
 // and of the view layer.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -35,6 +36,7 @@ namespace fnerf {
 using namespace ptx;
 
 constexpr int kTileM = 128;
+constexpr int kDefaultMlpCluster = 1;     // render kernel as single CTAs (1) or CTA pairs (2, see k_mlp_tc); FNERF_MLP_CLUSTER overrides
 constexpr int kStages = 3;
 constexpr int kTcThreads = 576;
 constexpr int kWorkerThreads = 512;
@@ -46,7 +48,7 @@ constexpr uint32_t kOffW = kOffPed + kKBlockBytes;              // weight stages
 constexpr uint32_t kOffHeads = kOffW + kStages * kBigChunkBytes;  // fp32 head weights (aux from kAuxWAlpha on)
 constexpr int kHeadFloats = kAuxFloats - kAuxWAlpha;
 constexpr uint32_t kOffBar = kOffHeads + kHeadFloats * 4;
-constexpr uint32_t kNumBars = 2 * kStages + 4 + 1 + 2;
+constexpr uint32_t kNumBars = 3 * (2 * kStages) + 4 + 1 + 2;   // room for the pair mode: 2*kStages x (full, empty, peer-weights) + act-ready, encodings, acc-full
 constexpr uint32_t kTcSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;  // + tmem ptr + alignment slack
 static_assert(kOffBar % 8 == 0, "barrier alignment");
 static_assert(kTcSmemBytes <= 227 * 1024, "shared memory budget");
@@ -151,17 +153,31 @@ __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, %0
 // named barrier of the two worker groups (8 warps) that share an activation K-block: pair 0 = groups 0, 1; pair 1 = groups 2, 3
 __device__ __forceinline__ void pair_bar_sync(uint32_t pair) { asm volatile("bar.sync %0, 256;" ::"r"(2u + pair) : "memory"); }
 
-template <bool kSave>
+// kCl == 2: CTA pair (thread-block cluster of 2, tcgen05 cta_group::2).  The pair runs two 128-sample tiles in
+// lock step as ONE M = 256 MMA stream issued by the leader (cluster rank 0): every CTA keeps its own tile (A operand,
+// TMEM accumulators, epilogue) but streams only ITS HALF of every weight chunk (N/2 rows of B); the tensor cores of the
+// two SMs exchange the halves.  Per SM that halves the bytes written into shared memory by the weight stream and the
+// bytes of B read back by the MMAs -- the two costs that A/B builds showed to limit the single-CTA kernel (streaming
+// half of each chunk: +6-8 %, none: +12 %).  Handshakes: both CTAs' epilogue / encoding warps arrive on the LEADER's
+// act-ready and encoding barriers (mbarrier.arrive.release.cluster on mapa addresses); the peer's otherwise idle MMA warp
+// relays "my half of stage s has landed" to the leader; tcgen05.commit multicasts stage-empty and accumulator-full to
+// both CTAs.  Both CTAs run the same number of tiles (a tile past the end is computed on clamped inputs, not stored).
+template <bool kSave, int kCl>
 __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar0 = base + kOffBar;
+  // pair mode streams half chunks: twice the stages of half the size cover the longer refill round trip
+  // (leader commit -> peer's empty barrier -> load -> peer's relay -> leader)
+  constexpr int kSt = kCl > 1 ? 2 * kStages : kStages;
+  constexpr uint32_t kStageBytes = kCl > 1 ? kBigChunkBytes / 2 : kBigChunkBytes;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto bar_act = [&](int kb) { return bar0 + 8u * (2 * kStages + kb); };
-  const uint32_t bar_pe = bar0 + 8u * (2 * kStages + 4);
-  auto bar_acc = [&](int a) { return bar0 + 8u * (2 * kStages + 5 + a); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kSt + s); };
+  auto bar_act = [&](int kb) { return bar0 + 8u * (2 * kSt + kb); };
+  const uint32_t bar_pe = bar0 + 8u * (2 * kSt + 4);
+  auto bar_acc = [&](int a) { return bar0 + 8u * (2 * kSt + 5 + a); };
+  auto bar_wpeer = [&](int s) { return bar0 + 8u * (2 * kSt + 7 + s); };   // pair: the peer's half of stage s has landed
   const uint32_t tmem_slot = bar0 + 8u * kNumBars;
   float* heads_s = reinterpret_cast<float*>(base_ptr + kOffHeads);   // index with (kAux* - kAuxWAlpha)
 
@@ -173,36 +189,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     for (int i = threadIdx.x; i < kHeadFloats; i += kTcThreads) heads_s[i] = aux_g[i];
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 8);     // one arrive per warp: 2 groups x 4 warps per K-block
-    mbar_init(bar_pe, 256);                                       // encoding groups 0 and 1
+    for (int s = 0; s < kSt; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); mbar_init(bar_wpeer(s), 1); }
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 8 * kCl);   // one arrive per warp: 2 groups x 4 warps per K-block (x CTAs)
+    mbar_init(bar_pe, 256 * kCl);                                     // encoding groups 0 and 1 (x CTAs)
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) {
+    if (kCl > 1) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
   __syncthreads();
+  if (kCl > 1) cluster_sync();               // no peer may arrive on barriers that are not initialised yet
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBar + 8 * kNumBars);
 
   const int64_t first_tile = blockIdx.x;
   const int64_t tile_stride = gridDim.x;
+  // every CTA runs n_iter tiles (identical across a cluster); without clusters that is exactly the tiles it owns
+  const int64_t n_iter = kCl > 1 ? (P.ntiles + tile_stride - 1) / tile_stride
+                                 : (P.ntiles > first_tile ? (P.ntiles - first_tile + tile_stride - 1) / tile_stride : 0);
+  [[maybe_unused]] const uint32_t cta_rank = kCl > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kClMask = (uint16_t)((1u << kCl) - 1u);
+  // pair mode: act-ready / encoding arrivals of BOTH CTAs go to the leader's barriers
+  [[maybe_unused]] const uint32_t lead_bar_act0 = kCl > 1 ? mapa_shared(bar_act(0), 0) : 0u;
+  [[maybe_unused]] const uint32_t lead_bar_pe = kCl > 1 ? mapa_shared(bar_pe, 0) : 0u;
 
   if (warp == 0) {
     // ================================ weight producer ==============================================
     if (lane == 0) {
       uint32_t wc = 0;
-      for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride) {
+      for (int64_t it = 0; it < n_iter; ++it) {
+        [[maybe_unused]] const int64_t tile = first_tile + it * tile_stride;
         for (int c = 0; c < kNumChunks; ++c, ++wc) {
-          const uint32_t s = wc % kStages;
-          mbar_wait(bar_empty(s), ((wc / kStages) & 1u) ^ 1u);
+          const uint32_t s = wc % kSt;
+          mbar_wait(bar_empty(s), ((wc / kSt) & 1u) ^ 1u);
           const uint32_t bytes = (uint32_t)chunk_bytes(c);
 #ifdef EXP_NOTMA
-          mbar_arrive(bar_full(s)); (void)bytes;
+          // experiment (tools/ab_tc.py): weights are streamed for the CTA's first tile only, afterwards the stages keep
+          // those (real, but stale) chunks -- bounds what removing the L2 -> SM weight traffic could buy
+          if (tile != first_tile) { mbar_arrive(bar_full(s)); continue; }
+#endif
+#ifdef EXP_HALFW
+          // experiment: only the first half of every chunk is streamed (the MMAs still read the whole, half-stale stage)
+          mbar_expect_tx(bar_full(s), bytes / 2);
+          bulk_g2s(base + kOffW + s * kStageBytes, P.packed + chunk_offset(c), bytes / 2, bar_full(s));
 #else
-          mbar_expect_tx(bar_full(s), bytes);
-          bulk_g2s(base + kOffW + s * kBigChunkBytes, P.packed + chunk_offset(c), bytes, bar_full(s));
+          if (kCl > 1) {                          // this CTA's N/2 rows of the chunk, at the start of the stage
+            const uint32_t part = bytes / 2;
+            mbar_expect_tx(bar_full(s), part);
+            bulk_g2s(base + kOffW + s * kStageBytes, P.packed + chunk_offset(c) + cta_rank * part, part, bar_full(s));
+          } else {
+            mbar_expect_tx(bar_full(s), bytes);
+            bulk_g2s(base + kOffW + s * kStageBytes, P.packed + chunk_offset(c), bytes, bar_full(s));
+          }
 #endif
         }
       }
@@ -218,9 +260,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     // The loop runs warp-uniformly on all 32 lanes and only the MMA / commit instructions are
     // predicated on one elected lane: with a divergent `if (lane == 0)` around the loop ptxas cannot
     // prove the descriptors uniform and wraps EVERY tcgen05.mma in an elect/R2UR waterfall loop.
-    {
-      constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256);
-      constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
+    if (kCl > 1 && cta_rank != 0) {
+      // peer of a CTA pair: no MMAs to issue; tell the leader when this CTA's half of a weight stage has landed
+      const uint32_t lead_wpeer0 = mapa_shared(bar_wpeer(0), 0);
+      uint32_t wc = 0;
+      for (int64_t it = 0; it < n_iter; ++it) {
+        for (int c = 0; c < kNumChunks; ++c, ++wc) {
+          const uint32_t s = wc % kSt;
+          mbar_wait(bar_full(s), (wc / kSt) & 1u);
+          if (lane == 0) mbar_arrive_cluster(lead_wpeer0 + 8u * s);
+          __syncwarp();
+        }
+      }
+    } else {
+      constexpr uint32_t idesc256 = umma_idesc_bf16(128 * kCl, 256);
+      constexpr uint32_t idesc128 = umma_idesc_bf16(128 * kCl, 128);
       uint32_t wc = 0, act_cnt = 0, tile_cnt = 0;
       [[maybe_unused]] uint32_t tslot = 0;   // tracer: slots [0,256): (before waits, operands ready, issued) per chunk
       const uint64_t desc_act = umma_desc_sw128(base + kOffAct);
@@ -229,22 +283,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
       const uint64_t desc_w = umma_desc_sw128(base + kOffW);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
       const uint32_t acc_addr[2] = {tmem_u, tmem_u + 256};
-      for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride, ++tile_cnt) {
+      for (int64_t it = 0; it < n_iter; ++it, ++tile_cnt) {
         mbar_wait(bar_pe, tile_cnt & 1u);
-        bool w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full(wc % kStages), (wc / kStages) & 1u));
+        bool w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full(wc % kSt), (wc / kSt) & 1u) &&
+                                                   (kCl == 1 || mbar_test_wait(bar_wpeer(wc % kSt), (wc / kSt) & 1u)));
         bool a_ready = true;
 #pragma unroll
         for (int c = 0; c < kNumChunks; ++c) {
           const MmaChunk op = mma_chunk(c);
-          const uint32_t s = wc % kStages;
+          const uint32_t s = wc % kSt;
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
           if (op.gated && !a_ready) mbar_wait(bar_act(op.kb), act_cnt & 1u);
-          if (!w_ready) mbar_wait(bar_full(s), (wc / kStages) & 1u);
+          if (!w_ready) {
+            mbar_wait(bar_full(s), (wc / kSt) & 1u);
+            if (kCl > 1) mbar_wait(bar_wpeer(s), (wc / kSt) & 1u);
+          }
           tc_fence_after();
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
           // probe the next chunk's barriers now; the answers are needed only after this chunk is issued
           const uint32_t act_next = act_cnt + ((op.gated && op.kb == 3) ? 1u : 0u);
-          w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full((wc + 1) % kStages), ((wc + 1) / kStages) & 1u));
+          w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full((wc + 1) % kSt), ((wc + 1) / kSt) & 1u) &&
+                                                (kCl == 1 || mbar_test_wait(bar_wpeer((wc + 1) % kSt), ((wc + 1) / kSt) & 1u)));
           if (c + 1 < kNumChunks) {
             const MmaChunk nx = mma_chunk(c + 1);
             a_ready = nx.gated ? __all_sync(0xffffffffu, mbar_test_wait(bar_act(nx.kb), act_next & 1u)) : true;
@@ -253,7 +312,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           }
           const uint64_t a_desc = (op.a_sel == 0 ? desc_act + (uint64_t)(op.kb * (kKBlockBytes >> 4))
                                                  : (op.a_sel == 1 ? desc_pe : desc_ped)) + (uint64_t)(2 * op.kstep0);
-          const uint64_t b_desc = desc_w + (uint64_t)(s * (kBigChunkBytes >> 4)) + (uint64_t)(2 * op.kstep0);
+          const uint64_t b_desc = desc_w + (uint64_t)(s * (kStageBytes >> 4)) + (uint64_t)(2 * op.kstep0);
           const uint32_t idesc = op.n128 ? idesc128 : idesc256;
           if (elect_one()) {
 #pragma unroll
@@ -261,10 +320,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
 #ifdef EXP_NOMMA
               if (P.M < 0)
 #endif
-              umma_bf16(acc_addr[op.acc], a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
-                        (op.fresh && ks == 0) ? 0u : 1u);
-            umma_commit(bar_empty(s));
-            if (op.commit_acc) umma_commit(bar_acc(op.acc));
+              if (kCl > 1) umma_bf16_pair(acc_addr[op.acc], a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
+                                          (op.fresh && ks == 0) ? 0u : 1u);
+              else umma_bf16(acc_addr[op.acc], a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
+                             (op.fresh && ks == 0) ? 0u : 1u);
+            if (kCl > 1) {
+              umma_commit_pair(bar_empty(s), kClMask);
+              if (op.commit_acc) umma_commit_pair(bar_acc(op.acc), kClMask);
+            } else {
+              umma_commit(bar_empty(s));
+              if (op.commit_acc) umma_commit(bar_acc(op.acc));
+            }
           }
           __syncwarp();
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
@@ -283,7 +349,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     [[maybe_unused]] uint32_t wtile = 0, wslot = 256 + grp * 64;   // tracer: 64 slots per group from 256
     const uint32_t act_row = base + kOffAct + row * 128u;
     uint8_t* ped_row_ptr = base_ptr + kOffPed + row * 128u;
-    for (int64_t tile = first_tile; tile < P.ntiles; tile += tile_stride) {
+    for (int64_t it = 0; it < n_iter; ++it) {
+      const int64_t tile = first_tile + it * tile_stride;     // >= ntiles only in a cluster's padding tiles: g >= M, nothing stored
       const int64_t g = tile * kTileM + row;
       const int64_t gc = g < P.M ? g : P.M - 1;
       const int64_t ray = gc / P.S;
@@ -318,7 +385,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           if (kSave) *reinterpret_cast<uint4*>(tape_tile + kTapeSlotPe * kKBlockBytes + row * 128u + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
         }
         fence_proxy_async_smem();
-        mbar_arrive(bar_pe);
+        if (kCl > 1) mbar_arrive_cluster(lead_bar_pe);
+        else mbar_arrive(bar_pe);
       } else if (grp == 1) {
         float d[32];
 #pragma unroll
@@ -351,7 +419,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           if (kSave) *reinterpret_cast<uint4*>(tape_tile + kTapeSlotPed * kKBlockBytes + row * 128u + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
         }
         fence_proxy_async_smem();
-        mbar_arrive(bar_pe);
+        if (kCl > 1) mbar_arrive_cluster(lead_bar_pe);
+        else mbar_arrive(bar_pe);
       }
 
       const float* rowbias = nullptr;
@@ -391,7 +460,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_act(kb));
+          if (lane == 0) {
+            if (kCl > 1) mbar_arrive_cluster(lead_bar_act0 + 8u * kb);
+            else mbar_arrive(bar_act(kb));
+          }
           if (kSave) {
             // Training tape: the 16 KB image of K-block kb is complete once the two groups that share it have
             // stored their halves.  Those 8 warps then copy it to the tape LINEARLY (2 KB per warp, 512
@@ -465,9 +537,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   // ---- teardown -----------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (kCl > 1) cluster_sync();               // the peer may still arrive on this CTA's barriers / its MMAs read this CTA's tiles
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kCl > 1) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -480,6 +554,46 @@ extern "C" int fnerf_debug_set_trace(long long* buf) {
 // tape == nullptr: render path.  tape != nullptr: training forward, every intermediate activation is also
 // streamed to the tape as K-block images plus one ReLU bitmask word per row and 32-column unit
 // (mlp_dgrad_tc.cu / mlp_bwd_tc.cu consume them).
+template <int kCl>
+static int launch_mlp_tc_cluster(const TcParams& P, cudaStream_t s) {
+  static int max_clusters[64] = {0};                 // 0 = not queried, < 0 = clusters unavailable
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kTcSmemBytes; cfg.stream = s; cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_clusters[dev] == 0) {
+    cudaError_t e = cudaFuncSetAttribute(k_mlp_tc<false, kCl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    int n = 0;
+    cfg.gridDim = dim3((unsigned)(num_sms() / kCl * kCl));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, k_mlp_tc<false, kCl>, &cfg);
+    max_clusters[dev] = (e == cudaSuccess && n > 0) ? n : -1;
+    (void)cudaGetLastError();
+  }
+  if (max_clusters[dev] < 0) return -1;              // caller falls back to the single-CTA kernel
+  int64_t clusters = max_clusters[dev];
+  const int64_t want = (P.ntiles + kCl - 1) / kCl;
+  if (clusters > want) clusters = want;
+  cfg.gridDim = dim3((unsigned)(clusters * kCl));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_mlp_tc<false, kCl>, P);
+  if (e != cudaSuccess) return set_error((int)e, "mlp_tc cluster launch: %s", cudaGetErrorString(e));
+  return check_launch("mlp_tc");
+}
+
+// render kernel as single CTAs (1) or CTA pairs (2): FNERF_MLP_CLUSTER overrides the default
+static int mlp_cluster_size() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FNERF_MLP_CLUSTER");
+    v = e ? atoi(e) : kDefaultMlpCluster;
+    if (v != 1 && v != 2) v = 1;
+  }
+  return v;
+}
+
 int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cudaStream_t s) {
   const int64_t M = a.R * a.S;
   if (M == 0) return 0;
@@ -488,8 +602,8 @@ int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cud
   cudaGetDevice(&dev);
   const int sv = tape != nullptr ? 1 : 0;
   if (dev >= 0 && dev < 64 && !attr_done[dev][sv]) {
-    cudaError_t e = sv ? cudaFuncSetAttribute(k_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)
-                       : cudaFuncSetAttribute(k_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    cudaError_t e = sv ? cudaFuncSetAttribute(k_mlp_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)
+                       : cudaFuncSetAttribute(k_mlp_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     if (e != cudaSuccess) return set_error((int)e, "mlp_tc attr: %s", cudaGetErrorString(e));
     attr_done[dev][sv] = true;
   }
@@ -500,10 +614,16 @@ int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cud
   P.raw = reinterpret_cast<float4*>(a.raw);
   P.M = M; P.S = (int)a.S; P.ntiles = (M + kTileM - 1) / kTileM; P.cond = a.cond;
   P.tape = tape; P.mask_tape = mask_tape;
+  if (!sv && P.ntiles >= 2 * (int64_t)num_sms()) {     // enough tiles per CTA for the shared weight stream to pay
+    const int cl = mlp_cluster_size();
+    int rc = -1;
+    if (cl == 2) rc = launch_mlp_tc_cluster<2>(P, s);
+    if (rc >= 0) return rc;
+  }
   int64_t blocks = num_sms();
   if (blocks > P.ntiles) blocks = P.ntiles;
-  if (sv) k_mlp_tc<true><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
-  else k_mlp_tc<false><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
+  if (sv) k_mlp_tc<true, 1><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
+  else k_mlp_tc<false, 1><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
   return check_launch("mlp_tc");
 }
 

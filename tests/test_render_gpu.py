@@ -271,3 +271,39 @@ def test_cfg4_shard_properties(F, cuda_device):
     assert zf.shape == (o.shape[0], 1024) and (zf[:, 1:] >= zf[:, :-1]).all()
     assert torch.isfinite(full["rgb"]).all() and full["acc"].max() <= 1 + 1e-5 and full["acc"].min() >= -1e-6
     assert torch.equal(half["rgb"], full["rgb"][:9001])
+
+
+def test_cta_pair_mode_is_bit_identical(cuda_device):
+    """FNERF_MLP_CLUSTER=2 runs the render kernel as CTA pairs (tcgen05 cta_group::2, M = 256 MMAs issued by the leader,
+    each CTA streaming half of every weight chunk).  Same arithmetic per element, so raw must match the default
+    single-CTA kernel bit for bit, including tile counts that are not a multiple of the grid and a ragged last tile.
+    (Separate processes: the mode is read once per process.)"""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, ".")
+import fashion_nerf_b200 as F
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(5)
+out = []
+for R, S in ((16384, 192), (5001, 77), (40000, 64)):      # 24576 / 3009 / 20000 tiles; 5001*77 leaves a ragged tile
+    o = (torch.rand(R, 3, generator=g) * 2 - 1).to(dev); d = torch.randn(R, 3, generator=g).to(dev)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0].to(dev)
+    net = F.NerfNetwork.random(3, dev)
+    vd, _ = F.ops.ray_setup(d)
+    raw = F.ops.mlp_fwd(net.packed, o, d, vd, z, precision="bf16")
+    torch.cuda.synchronize()
+    out.append(raw.view(torch.int32).to(torch.int64).sum().item())
+    out.append(int(torch.isfinite(raw).all()))
+print("CHK", out)
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("1", "2"):
+        env = dict(os.environ, FNERF_MLP_CLUSTER=mode)
+        p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[mode] = [l for l in p.stdout.splitlines() if l.startswith("CHK")][0]
+    assert res["1"] == res["2"], res
