@@ -48,26 +48,26 @@ FN_HD int64_t flat_count(int cond) { return flat_weight_offset(kNumLayers, cond)
 // image one bulk-TMA copy drops into a pipeline stage.  Chunk kinds (chunk_desc):
 //   TRUNK  W[:, base + 64*kb ..]                      A operand = activation K-block kb
 //   XYZ    W[:, 0:63] (+ zero column)                 A operand = xyz-encoding tile      (layers 0, 5)
-//   BIAS   zeros except col 27 = bf16(b), col 28 = bf16(b - bf16(b))
+//   BIAS   one K = 16 step, 8 KB, stored MN-major (N contiguous: 4 groups of 64 outputs x 16 K rows x 128 B,
+//          128-byte swizzle; byte (n, k) at (n/64)*2048 + k*128 + ((((n%64)/8) ^ (k&7)) << 4) + (n%8)*2):
+//          zeros except K row 11 = bf16(b), row 12 = bf16(b - bf16(b)).
 //                                                     A operand = K-step 1 (cols 16..31) of the
 //          direction-encoding tile, whose cols 27, 28 hold 1.0 -> the fp32 accumulator receives the
-//          bias to ~16 mantissa bits and the epilogue needs no bias add
+//          bias to ~16 mantissa bits and the epilogue needs no bias add.  (A K-major BIAS chunk would be a
+//          full 32 KB of which one K-step is read: 20 % of the weight stream.)
 //   DIR    Wv[:, 256:283] in cols 0..26, view-layer bias hi/lo in cols 27, 28 (view layer only)
 // Order: L0 {XYZ,BIAS}; L1..L4 {k0..k3,BIAS}; L5 {XYZ,k0..k3,BIAS}; L6,L7 {k0..k3,BIAS};
 // feature {k0..k3,BIAS}; views {k0..k3 (128 rows), DIR (128 rows)}.
 constexpr int kChunkK = 64;
-constexpr int kBigChunks = 43;
-constexpr int kSmallChunks = 5;
-constexpr int kNumChunks = kBigChunks + kSmallChunks;
-constexpr int kBigChunkBytes = 256 * kChunkK * 2;   // 32768
+constexpr int kNumChunks = 48;
+constexpr int kFirstViewChunk = 43;                 // chunks 43..47: the view layer's 128-row chunks
+constexpr int kNumBiasChunks = 9;
+constexpr int kBigChunkBytes = 256 * kChunkK * 2;   // 32768 (also the pipeline stage size)
 constexpr int kSmallChunkBytes = 128 * kChunkK * 2; // 16384
-constexpr int kBiasColHi = 27, kBiasColLo = 28;     // inside the direction tile / BIAS and DIR chunks
-constexpr int64_t kSecABytes = (int64_t)kBigChunks * kBigChunkBytes + (int64_t)kSmallChunks * kSmallChunkBytes;
-FN_HD int64_t chunk_offset(int c) {
-  return c < kBigChunks ? (int64_t)c * kBigChunkBytes
-                        : (int64_t)kBigChunks * kBigChunkBytes + (int64_t)(c - kBigChunks) * kSmallChunkBytes;
-}
-FN_HD int chunk_bytes(int c) { return c < kBigChunks ? kBigChunkBytes : kSmallChunkBytes; }
+constexpr int kBiasChunkBytes = 256 * 16 * 2;       // 8192
+constexpr int kBiasColHi = 27, kBiasColLo = 28;     // inside the direction tile / DIR chunk; K rows 11, 12 of a BIAS chunk
+constexpr int64_t kSecABytes = (int64_t)(kFirstViewChunk - kNumBiasChunks) * kBigChunkBytes + (int64_t)kNumBiasChunks * kBiasChunkBytes +
+                               (int64_t)(kNumChunks - kFirstViewChunk) * kSmallChunkBytes;
 
 enum { CHUNK_TRUNK = 0, CHUNK_XYZ = 1, CHUNK_BIAS = 2, CHUNK_DIR = 3 };
 struct ChunkDesc { int layer; int kind; int kb; };   // layer = flat layer id (0..7 trunk, 9 feature, 10 views)
@@ -82,6 +82,19 @@ FN_HD constexpr ChunkDesc chunk_desc(int c) {
   if (c <= 42) return {9, c - 38 == 4 ? CHUNK_BIAS : CHUNK_TRUNK, c - 38};
   if (c <= 46) return {10, CHUNK_TRUNK, c - 43};
   return {10, CHUNK_DIR, 0};
+}
+
+FN_HD constexpr int chunk_bytes(int c) {
+  return c >= kFirstViewChunk ? kSmallChunkBytes : (chunk_desc(c).kind == CHUNK_BIAS ? kBiasChunkBytes : kBigChunkBytes);
+}
+FN_HD constexpr int64_t chunk_offset(int c) {
+  int64_t off = 0;
+  for (int i = 0; i < c; ++i) off += chunk_bytes(i);
+  return off;
+}
+// byte offset of element (output n, K row k < 16) inside a BIAS chunk
+FN_HD uint32_t bias_chunk_offset(uint32_t n, uint32_t k) {
+  return (n >> 6) * 2048u + k * 128u + ((((n & 63u) >> 3) ^ (k & 7u)) << 4) + (n & 7u) * 2u;
 }
 
 // Section B: fp32 "aux" (biases and the two tiny heads), offsets in floats.

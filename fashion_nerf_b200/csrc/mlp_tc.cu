@@ -73,6 +73,7 @@ struct MmaChunk {
   int fresh;       // first MMA overwrites the accumulator
   int gated;       // wait for the epilogue's act-ready[kb]
   int commit_acc;  // last chunk of a layer: commit to acc-full[acc]
+  int bias;        // B = compact MN-major BIAS chunk (one K-step at the start of the stage)
 };
 __host__ __device__ constexpr int layer_step(int flat_layer) { return flat_layer < 8 ? flat_layer : (flat_layer == 9 ? 8 : 9); }
 __host__ __device__ constexpr MmaChunk mma_chunk(int c) {
@@ -80,10 +81,10 @@ __host__ __device__ constexpr MmaChunk mma_chunk(int c) {
   const int acc = layer_step(d.layer) & 1;
   const bool first = c == 0 || chunk_desc(c - 1).layer != d.layer;
   const bool last = c == kNumChunks - 1 || chunk_desc(c + 1).layer != d.layer;
-  if (d.kind == CHUNK_TRUNK) return {0, d.kb, 0, 4, d.layer == 10, acc, first, 1, last};
-  if (d.kind == CHUNK_XYZ) return {1, 0, 0, 4, 0, acc, first, 0, last};
-  if (d.kind == CHUNK_BIAS) return {2, 0, 1, 1, 0, acc, first, 0, last};     // K-step 1 = cols 16..31 (ones at 27, 28)
-  return {2, 0, 0, 2, 1, acc, first, 0, last};                              // CHUNK_DIR: cols 0..31
+  if (d.kind == CHUNK_TRUNK) return {0, d.kb, 0, 4, d.layer == 10, acc, first, 1, last, 0};
+  if (d.kind == CHUNK_XYZ) return {1, 0, 0, 4, 0, acc, first, 0, last, 0};
+  if (d.kind == CHUNK_BIAS) return {2, 0, 1, 1, 0, acc, first, 0, last, 1};  // A: K-step 1 = cols 16..31 (ones at 27, 28)
+  return {2, 0, 0, 2, 1, acc, first, 0, last, 0};                           // CHUNK_DIR: cols 0..31
 }
 
 struct TcParams {
@@ -223,10 +224,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
       uint32_t wc = 0;
       for (int64_t it = 0; it < n_iter; ++it) {
         [[maybe_unused]] const int64_t tile = first_tile + it * tile_stride;
+        uint32_t coff = 0;                       // chunk_offset(c), accumulated
         for (int c = 0; c < kNumChunks; ++c, ++wc) {
           const uint32_t s = wc % kSt;
-          mbar_wait(bar_empty(s), ((wc / kSt) & 1u) ^ 1u);
           const uint32_t bytes = (uint32_t)chunk_bytes(c);
+          const uint8_t* csrc = P.packed + coff;
+          coff += bytes;
+          mbar_wait(bar_empty(s), ((wc / kSt) & 1u) ^ 1u);
 #ifdef EXP_NOTMA
           // experiment (tools/ab_tc.py): weights are streamed for the CTA's first tile only, afterwards the stages keep
           // those (real, but stale) chunks -- bounds what removing the L2 -> SM weight traffic could buy
@@ -235,15 +239,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
 #ifdef EXP_HALFW
           // experiment: only the first half of every chunk is streamed (the MMAs still read the whole, half-stale stage)
           mbar_expect_tx(bar_full(s), bytes / 2);
-          bulk_g2s(base + kOffW + s * kStageBytes, P.packed + chunk_offset(c), bytes / 2, bar_full(s));
+          bulk_g2s(base + kOffW + s * kStageBytes, csrc, bytes / 2, bar_full(s));
 #else
           if (kCl > 1) {                          // this CTA's N/2 rows of the chunk, at the start of the stage
             const uint32_t part = bytes / 2;
             mbar_expect_tx(bar_full(s), part);
-            bulk_g2s(base + kOffW + s * kStageBytes, P.packed + chunk_offset(c) + cta_rank * part, part, bar_full(s));
+            bulk_g2s(base + kOffW + s * kStageBytes, csrc + cta_rank * part, part, bar_full(s));
           } else {
             mbar_expect_tx(bar_full(s), bytes);
-            bulk_g2s(base + kOffW + s * kStageBytes, P.packed + chunk_offset(c), bytes, bar_full(s));
+            bulk_g2s(base + kOffW + s * kStageBytes, csrc, bytes, bar_full(s));
           }
 #endif
         }
@@ -275,12 +279,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     } else {
       constexpr uint32_t idesc256 = umma_idesc_bf16(128 * kCl, 256);
       constexpr uint32_t idesc128 = umma_idesc_bf16(128 * kCl, 128);
+      constexpr uint32_t idesc256b = umma_idesc_bf16(128 * kCl, 256) | (1u << 16);   // B operand MN-major (BIAS chunks)
       uint32_t wc = 0, act_cnt = 0, tile_cnt = 0;
       [[maybe_unused]] uint32_t tslot = 0;   // tracer: slots [0,256): (before waits, operands ready, issued) per chunk
       const uint64_t desc_act = umma_desc_sw128(base + kOffAct);
       const uint64_t desc_pe = umma_desc_sw128(base + kOffPe);
       const uint64_t desc_ped = umma_desc_sw128(base + kOffPed);
       const uint64_t desc_w = umma_desc_sw128(base + kOffW);
+      const uint64_t desc_wb = umma_desc_mn_sw128(base + kOffW, 2048);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
       const uint32_t acc_addr[2] = {tmem_u, tmem_u + 256};
       for (int64_t it = 0; it < n_iter; ++it, ++tile_cnt) {
@@ -312,8 +318,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           }
           const uint64_t a_desc = (op.a_sel == 0 ? desc_act + (uint64_t)(op.kb * (kKBlockBytes >> 4))
                                                  : (op.a_sel == 1 ? desc_pe : desc_ped)) + (uint64_t)(2 * op.kstep0);
-          const uint64_t b_desc = desc_w + (uint64_t)(s * (kStageBytes >> 4)) + (uint64_t)(2 * op.kstep0);
-          const uint32_t idesc = op.n128 ? idesc128 : idesc256;
+          // BIAS chunk: MN-major K = 16 tile at the start of the stage (4 groups of 64 outputs, 2 KB apart; per CTA of a pair: 2)
+          const uint64_t b_desc = op.bias ? desc_wb + (uint64_t)(s * (kStageBytes >> 4))
+                                          : desc_w + (uint64_t)(s * (kStageBytes >> 4)) + (uint64_t)(2 * op.kstep0);
+          const uint32_t idesc = op.bias ? idesc256b : (op.n128 ? idesc128 : idesc256);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < op.ksteps; ++ks)

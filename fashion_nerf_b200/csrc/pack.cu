@@ -5,33 +5,42 @@
 
 namespace fnerf {
 
+// one CTA per chunk
 __global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict__ packed, int cond) {
-  const int64_t total = (int64_t)kBigChunks * 256 * 64 + (int64_t)kSmallChunks * 128 * 64;
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  int c, within;
-  const int64_t big = (int64_t)kBigChunks * 256 * 64;
-  if (e < big) { c = (int)(e / (256 * 64)); within = (int)(e % (256 * 64)); }
-  else { c = kBigChunks + (int)((e - big) / (128 * 64)); within = (int)((e - big) % (128 * 64)); }
-  const int r = within >> 6, k = within & 63;          // output feature r, K column k of the chunk
+  const int c = blockIdx.x;
   const ChunkDesc cd = chunk_desc(c);
   const LayerDim d = layer_dim(cd.layer, cond);
   const float* W = flat + flat_weight_offset(cd.layer, cond);
   const float* bvec = flat + flat_bias_offset(cd.layer, cond);
-  float v = 0.0f;
-  if (cd.kind == CHUNK_TRUNK) {
-    const int base = (cd.layer == 5) ? kPE + (cond ? kCond : 0) : 0;
-    v = W[(int64_t)r * d.in + base + cd.kb * 64 + k];
-  } else if (cd.kind == CHUNK_XYZ) {
-    if (k < kPE) v = W[(int64_t)r * d.in + k];
-  } else {                                             // BIAS / DIR: bias as bf16 hi + lo
-    if (cd.kind == CHUNK_DIR && k < kPED) v = W[(int64_t)r * d.in + kW + k];
-    const float b = bvec[r];
-    const float hi = __bfloat162float(__float2bfloat16_rn(b));
-    if (k == kBiasColHi) v = hi;
-    if (k == kBiasColLo) v = b - hi;
+  uint8_t* dst = packed + chunk_offset(c);
+  if (cd.kind == CHUNK_BIAS) {                            // MN-major K = 16 tile: K rows 11 / 12 = bias hi / lo
+    for (int e = threadIdx.x; e < 256 * 16; e += blockDim.x) {
+      const int n = e >> 4, k = e & 15;
+      const float b = bvec[n];
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      const float v = k == kBiasColHi - 16 ? hi : (k == kBiasColLo - 16 ? b - hi : 0.0f);
+      *reinterpret_cast<__nv_bfloat16*>(dst + bias_chunk_offset((uint32_t)n, (uint32_t)k)) = __float2bfloat16_rn(v);
+    }
+    return;
   }
-  *reinterpret_cast<__nv_bfloat16*>(packed + chunk_offset(c) + sw128_offset(r, k)) = __float2bfloat16_rn(v);
+  const int rows = c >= kFirstViewChunk ? 128 : 256;
+  for (int e = threadIdx.x; e < rows * 64; e += blockDim.x) {
+    const int r = e >> 6, k = e & 63;                     // output feature r, K column k of the chunk
+    float v = 0.0f;
+    if (cd.kind == CHUNK_TRUNK) {
+      const int base = (cd.layer == 5) ? kPE + (cond ? kCond : 0) : 0;
+      v = W[(int64_t)r * d.in + base + cd.kb * 64 + k];
+    } else if (cd.kind == CHUNK_XYZ) {
+      if (k < kPE) v = W[(int64_t)r * d.in + k];
+    } else {                                              // DIR: view-layer weights of the direction encoding + bias hi / lo
+      if (k < kPED) v = W[(int64_t)r * d.in + kW + k];
+      const float b = bvec[r];
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      if (k == kBiasColHi) v = hi;
+      if (k == kBiasColLo) v = b - hi;
+    }
+    *reinterpret_cast<__nv_bfloat16*>(dst + sw128_offset(r, k)) = __float2bfloat16_rn(v);
+  }
 }
 
 // Section E: transposed chunks for dgrad: chunk row k = input feature, column j = output feature 64*kb + j
@@ -106,8 +115,7 @@ __global__ void k_unpack(const uint8_t* __restrict__ packed, float* __restrict__
 
 int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s) {
   uint8_t* p = reinterpret_cast<uint8_t*>(packed);
-  const int64_t total = (int64_t)kBigChunks * 256 * 64 + (int64_t)kSmallChunks * 128 * 64;
-  k_pack_bf16<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(flat, p, cond);
+  k_pack_bf16<<<kNumChunks, 256, 0, s>>>(flat, p, cond);
   k_pack_aux<<<(kAuxFloats + 255) / 256, 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecBOffset), cond);
   int64_t nmax = 0;
   for (int j = 0; j < 10; ++j) {

@@ -155,6 +155,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // Instruction descriptor, .kind::f16: D = fp32, A = B = bf16, both K-major, dense.
+// MN-major shared-memory matrix descriptor, 128-byte swizzle: 64 contiguous MN elements per 128-byte row,
+// rows = K; LBO = byte distance between 64-element MN groups, SBO = byte distance between 8-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
