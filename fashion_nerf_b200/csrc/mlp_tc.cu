@@ -42,9 +42,11 @@ constexpr int kTcThreads = 576;
 constexpr int kWorkerThreads = 512;
 constexpr uint32_t kKBlockBytes = kTileM * 128;                 // 16 KB: 128 rows x 64 bf16
 constexpr uint32_t kOffAct = 0;                                 // 4 K-blocks
-constexpr uint32_t kOffPe = 4 * kKBlockBytes;                   // xyz encoding (63 -> 64)
-constexpr uint32_t kOffPed = kOffPe + kKBlockBytes;             // direction encoding (27) + ones (cols 27, 28)
-constexpr uint32_t kOffW = kOffPed + kKBlockBytes;              // weight stages
+constexpr uint32_t kOffPe = 4 * kKBlockBytes;                   // xyz encoding (63 -> 64), two buffers (tile parity)
+constexpr uint32_t kOffPed = kOffPe + 2 * kKBlockBytes;         // direction encoding (27) + ones (cols 27, 28) for the view layer's DIR chunk
+constexpr uint32_t kOffOnes = kOffPed + kKBlockBytes;           // constant K = 16 A tile of the BIAS MMAs: 128 x 16, MN-major, ones in K rows 11, 12
+constexpr uint32_t kOnesBytes = 128 * 16 * 2;
+constexpr uint32_t kOffW = kOffOnes + kOnesBytes;               // weight stages
 constexpr uint32_t kOffHeads = kOffW + kStages * kBigChunkBytes;  // fp32 head weights (aux from kAuxWAlpha on)
 constexpr int kHeadFloats = kAuxFloats - kAuxWAlpha;
 constexpr uint32_t kOffBar = kOffHeads + kHeadFloats * 4;
@@ -64,7 +66,7 @@ __device__ long long* g_trace_buf = nullptr;
 
 // The MMA schedule of one tile, derived from the packed chunk order (layout.h chunk_desc).
 struct MmaChunk {
-  int a_sel;       // 0 = activation K-block kb, 1 = xyz tile, 2 = direction tile
+  int a_sel;       // 0 = activation K-block kb, 1 = xyz tile, 2 = direction tile, 3 = constant ones tile (MN-major)
   int kb;          // activation K-block (also the act-ready barrier to honour when `gated`)
   int kstep0;      // first K=16 step inside the A tile / weight chunk
   int ksteps;      // number of K=16 MMAs
@@ -83,7 +85,7 @@ __host__ __device__ constexpr MmaChunk mma_chunk(int c) {
   const bool last = c == kNumChunks - 1 || chunk_desc(c + 1).layer != d.layer;
   if (d.kind == CHUNK_TRUNK) return {0, d.kb, 0, 4, d.layer == 10, acc, first, 1, last, 0};
   if (d.kind == CHUNK_XYZ) return {1, 0, 0, 4, 0, acc, first, 0, last, 0};
-  if (d.kind == CHUNK_BIAS) return {2, 0, 1, 1, 0, acc, first, 0, last, 1};  // A: K-step 1 = cols 16..31 (ones at 27, 28)
+  if (d.kind == CHUNK_BIAS) return {3, 0, 0, 1, 0, acc, first, 0, last, 1};  // A: the constant ones tile
   return {2, 0, 0, 2, 1, acc, first, 0, last, 0};                           // CHUNK_DIR: cols 0..31
 }
 
@@ -189,10 +191,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     const float* aux_g = reinterpret_cast<const float*>(P.packed + kSecBOffset) + kAuxWAlpha;
     for (int i = threadIdx.x; i < kHeadFloats; i += kTcThreads) heads_s[i] = aux_g[i];
   }
+  // constant A operand of the BIAS MMAs: ones in K rows 11 and 12 (= columns 27, 28 of a K-step-1 view), zeros elsewhere
+  for (int e = threadIdx.x; e < 128 * 16; e += kTcThreads) {
+    const uint32_t m = (uint32_t)e >> 4, k = (uint32_t)e & 15u;
+    *reinterpret_cast<unsigned short*>(base_ptr + kOffOnes + bias_chunk_offset(m, k)) =
+        (k == (uint32_t)(kBiasColHi - 16) || k == (uint32_t)(kBiasColLo - 16)) ? (unsigned short)0x3F80 : (unsigned short)0;
+  }
+  fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSt; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); mbar_init(bar_wpeer(s), 1); }
     for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 8 * kCl);   // one arrive per warp: 2 groups x 4 warps per K-block (x CTAs)
-    mbar_init(bar_pe, 256 * kCl);                                     // encoding groups 0 and 1 (x CTAs)
+    mbar_init(bar_pe, 128 * kCl);                                     // xyz-encoding group (x CTAs)
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
     fence_barrier_init();
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     } else {
       constexpr uint32_t idesc256 = umma_idesc_bf16(128 * kCl, 256);
       constexpr uint32_t idesc128 = umma_idesc_bf16(128 * kCl, 128);
-      constexpr uint32_t idesc256b = umma_idesc_bf16(128 * kCl, 256) | (1u << 16);   // B operand MN-major (BIAS chunks)
+      constexpr uint32_t idesc256b = umma_idesc_bf16(128 * kCl, 256) | (1u << 15) | (1u << 16);   // BIAS MMAs: A (ones) and B MN-major
       uint32_t wc = 0, act_cnt = 0, tile_cnt = 0;
       [[maybe_unused]] uint32_t tslot = 0;   // tracer: slots [0,256): (before waits, operands ready, issued) per chunk
       const uint64_t desc_act = umma_desc_sw128(base + kOffAct);
@@ -287,6 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
       const uint64_t desc_ped = umma_desc_sw128(base + kOffPed);
       const uint64_t desc_w = umma_desc_sw128(base + kOffW);
       const uint64_t desc_wb = umma_desc_mn_sw128(base + kOffW, 2048);
+      const uint64_t desc_ones = umma_desc_mn_sw128(base + kOffOnes, 2048);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // provably warp-uniform
       const uint32_t acc_addr[2] = {tmem_u, tmem_u + 256};
       for (int64_t it = 0; it < n_iter; ++it, ++tile_cnt) {
@@ -316,8 +326,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           } else {
             a_ready = true;
           }
-          const uint64_t a_desc = (op.a_sel == 0 ? desc_act + (uint64_t)(op.kb * (kKBlockBytes >> 4))
-                                                 : (op.a_sel == 1 ? desc_pe : desc_ped)) + (uint64_t)(2 * op.kstep0);
+          const uint64_t a_desc = op.a_sel == 3 ? desc_ones
+                                  : (op.a_sel == 0 ? desc_act + (uint64_t)(op.kb * (kKBlockBytes >> 4))
+                                                   : (op.a_sel == 1 ? desc_pe + (uint64_t)((tile_cnt & 1u) * (kKBlockBytes >> 4)) : desc_ped)) +
+                                        (uint64_t)(2 * op.kstep0);
           // BIAS chunk: MN-major K = 16 tile at the start of the stage (4 groups of 64 outputs, 2 KB apart; per CTA of a pair: 2)
           const uint64_t b_desc = op.bias ? desc_wb + (uint64_t)(s * (kStageBytes >> 4))
                                           : desc_w + (uint64_t)(s * (kStageBytes >> 4)) + (uint64_t)(2 * op.kstep0);
@@ -357,6 +369,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     [[maybe_unused]] uint32_t wtile = 0, wslot = 256 + grp * 64;   // tracer: 64 slots per group from 256
     const uint32_t act_row = base + kOffAct + row * 128u;
     uint8_t* ped_row_ptr = base_ptr + kOffPed + row * 128u;
+    // xyz encoding of this thread's row of tile `tile_n` into xyz buffer `buf` (group 0): sincos once per coordinate,
+    // then the double-angle recurrence per octave; arrives on the encoding barrier
+    auto compute_pe = [&](int64_t tile_n, uint32_t buf) {
+      const int64_t gn = tile_n * kTileM + row;
+      const int64_t gcn = gn < P.M ? gn : P.M - 1;
+      const int64_t rayn = gcn / P.S;
+      const float zv = P.z[gcn];
+      float f[64];
+      f[63] = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float p = __fadd_rn(P.rays_o[3 * rayn + c], __fmul_rn(P.rays_d[3 * rayn + c], zv));
+        f[c] = p;
+        float sn, cs;
+        sincosf(p, &sn, &cs);
+#pragma unroll
+        for (int k = 0; k < kLX; ++k) {
+          f[3 + 6 * k + c] = sn;
+          f[3 + 6 * k + 3 + c] = cs;
+          const float s2 = 2.0f * sn * cs;
+          cs = 1.0f - 2.0f * sn * sn;
+          sn = s2;
+        }
+      }
+      const uint32_t pe_row = base + kOffPe + buf * kKBlockBytes + row * 128u;
+      [[maybe_unused]] uint8_t* tape_n = kSave ? P.tape + (size_t)tile_n * kTapeFwdSlots * kKBlockBytes : nullptr;
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16) {
+        const uint4 pk = make_uint4(pack_bf16(f[c16 * 8 + 0], f[c16 * 8 + 1]), pack_bf16(f[c16 * 8 + 2], f[c16 * 8 + 3]),
+                                    pack_bf16(f[c16 * 8 + 4], f[c16 * 8 + 5]), pack_bf16(f[c16 * 8 + 6], f[c16 * 8 + 7]));
+        st_shared_v4(pe_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
+        if (kSave) *reinterpret_cast<uint4*>(tape_n + kTapeSlotPe * kKBlockBytes + row * 128u + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
+      }
+      fence_proxy_async_smem();
+      if (kCl > 1) mbar_arrive_cluster(lead_bar_pe);
+      else mbar_arrive(bar_pe);
+    };
     for (int64_t it = 0; it < n_iter; ++it) {
       const int64_t tile = first_tile + it * tile_stride;     // >= ntiles only in a cluster's padding tiles: g >= M, nothing stored
       const int64_t g = tile * kTileM + row;
@@ -364,42 +413,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
       const int64_t ray = gc / P.S;
       [[maybe_unused]] uint32_t* mask_row = kSave ? P.mask_tape + (size_t)tile * (kMaskUnits * 128) + row : nullptr;
       [[maybe_unused]] uint8_t* tape_tile = kSave ? P.tape + (size_t)tile * kTapeFwdSlots * kKBlockBytes : nullptr;
-      // ---- positional encodings (A.3): sincos once, then double-angle recurrence per octave -----
-      if (grp == 0) {
-        const float zv = P.z[gc];
-        float f[64];
-        f[63] = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float p = __fadd_rn(P.rays_o[3 * ray + c], __fmul_rn(P.rays_d[3 * ray + c], zv));
-          f[c] = p;
-          float sn, cs;
-          sincosf(p, &sn, &cs);
-#pragma unroll
-          for (int k = 0; k < kLX; ++k) {
-            f[3 + 6 * k + c] = sn;
-            f[3 + 6 * k + 3 + c] = cs;
-            const float s2 = 2.0f * sn * cs;
-            cs = 1.0f - 2.0f * sn * sn;
-            sn = s2;
-          }
-        }
-        const uint32_t pe_row = base + kOffPe + row * 128u;
-#pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          const uint4 pk = make_uint4(pack_bf16(f[c16 * 8 + 0], f[c16 * 8 + 1]), pack_bf16(f[c16 * 8 + 2], f[c16 * 8 + 3]),
-                                      pack_bf16(f[c16 * 8 + 4], f[c16 * 8 + 5]), pack_bf16(f[c16 * 8 + 6], f[c16 * 8 + 7]));
-          st_shared_v4(pe_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
-          if (kSave) *reinterpret_cast<uint4*>(tape_tile + kTapeSlotPe * kKBlockBytes + row * 128u + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
-        }
-        fence_proxy_async_smem();
-        if (kCl > 1) mbar_arrive_cluster(lead_bar_pe);
-        else mbar_arrive(bar_pe);
-      } else if (grp == 1) {
+      // ---- encodings (A.3).  The xyz tile of tile t+1 is built by group 0 while tile t runs (after its step-0
+      // epilogue, in time the workers would otherwise spend waiting for the next accumulator) into the other xyz
+      // buffer, so the first MMAs of a tile never wait for sincos.  The direction tile is needed by the view layer
+      // only (the BIAS MMAs multiply the constant ones tile), so group 1 builds it at the start of the tile, off the
+      // critical path; its stores are published by the fence below and ordered by the group's act-ready arrivals.
+      if (grp == 0 && it == 0) compute_pe(tile, 0u);
+      if (grp == 1) {
         float d[32];
 #pragma unroll
         for (int i = kPED; i < 32; ++i) d[i] = 0.0f;
-        d[kBiasColHi] = 1.0f;               // the two "ones" columns every layer's BIAS chunk multiplies
+        d[kBiasColHi] = 1.0f;               // the two "ones" columns the DIR chunk's bias rows multiply
         d[kBiasColLo] = 1.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -427,8 +451,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           if (kSave) *reinterpret_cast<uint4*>(tape_tile + kTapeSlotPed * kKBlockBytes + row * 128u + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
         }
         fence_proxy_async_smem();
-        if (kCl > 1) mbar_arrive_cluster(lead_bar_pe);
-        else mbar_arrive(bar_pe);
       }
 
       const float* rowbias = nullptr;
@@ -487,6 +509,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           }
           FN_TRACE(wtile == 2 && row == 0, wslot++);
         }
+        // next tile's xyz encodings, in the shadow of layer 1's MMAs (the buffer's last reader, layer 5 of the tile
+        // before this one, completed long ago)
+        if (step == 0 && grp == 0 && it + 1 < n_iter) compute_pe(tile + tile_stride, (uint32_t)((it + 1) & 1));
       }
       // ---- view layer epilogue + rgb head: each group reduces 32 of the 128 columns ---------------
       {
