@@ -165,6 +165,17 @@ int fnerf_adam_step(float* params, const float* grad, float* exp_avg, float* exp
   return launch_adam(params, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream);
 }
 
+int fnerf_allreduce_adam_step(const float* const* peer_grads, int world, int64_t offset, float* params, float* exp_avg,
+                              float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                              float grad_scale, fnerf_stream_t stream) {
+  FN_REQUIRE(n >= 0 && step >= 1 && offset >= 0, FNERF_ERR_SIZE, "allreduce_adam_step: bad n=%lld step=%lld", (long long)n, (long long)step);
+  FN_REQUIRE(world >= 1 && world <= 64, FNERF_ERR_SIZE, "allreduce_adam_step: bad world=%d", world);
+  if (n == 0) return 0;
+  FN_REQUIRE(peer_grads && params && exp_avg && exp_avg_sq, FNERF_ERR_NULL, "allreduce_adam_step: null pointer");
+  return launch_allreduce_adam(peer_grads, world, offset, params, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale,
+                               (cudaStream_t)stream);
+}
+
 int64_t fnerf_mlp_tape_bytes(int64_t R, int64_t S) { return mlp_tape_bytes(R * S); }
 int64_t fnerf_mlp_bwd_tape_workspace_bytes(int64_t R, int64_t S) { return mlp_bwd_from_tape_workspace_bytes(R * S); }
 

@@ -51,6 +51,8 @@ int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, c
                          int64_t S, int white, cudaStream_t s);
 int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s);
 int launch_unpack(const void* packed, float* flat, int cond, cudaStream_t s);
+int launch_allreduce_adam(const float* const* peer_grads, int world, int64_t offset, float* p, float* m, float* v, int64_t n, float lr,
+                          float b1, float b2, float eps, int64_t t, float grad_scale, cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int64_t t,
                 float grad_scale, cudaStream_t s);
 int launch_cond_project(const void* packed, const float* cond, float* proj, int64_t C, cudaStream_t s);

@@ -157,6 +157,34 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float l
   return check_launch("adam_step");
 }
 
+// Gradient all-reduce fused with Adam over peer memory (NVLink / NVSwitch P2P loads): every rank reads element i of all
+// `world` ranks' gradient buffers (same rank order everywhere -> bit-identical sums -> bit-identical replicas), scales,
+// and applies Adam to its own parameters.  The reduced gradient is never written anywhere.
+__global__ void __launch_bounds__(256) k_allreduce_adam(const float* const* __restrict__ peer_grads, int world, int64_t offset,
+                                                        float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                        float b1, float b2, float one_minus_b1, float one_minus_b2, float step_size,
+                                                        float inv_bc2, float eps, float grad_scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = 0.0f;
+  for (int r = 0; r < world; ++r) g += __ldcv(peer_grads[r] + offset + i);     // volatile-cached: peers just wrote these
+  const float gi = g * grad_scale;
+  const float mi = fmaf(one_minus_b1, gi, m[i] * b1);
+  const float vi = fmaf(one_minus_b2 * gi, gi, v[i] * b2);
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= step_size * mi / (sqrtf(vi * inv_bc2) + eps);
+}
+
+int launch_allreduce_adam(const float* const* peer_grads, int world, int64_t offset, float* p, float* m, float* v, int64_t n, float lr,
+                          float b1, float b2, float eps, int64_t t, float grad_scale, cudaStream_t s) {
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+  k_allreduce_adam<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(peer_grads, world, offset, p, m, v, n, b1, b2, 1.0f - b1, 1.0f - b2,
+                                                                 (float)(lr / bc1), (float)(1.0 / bc2), eps, grad_scale);
+  return check_launch("allreduce_adam_step");
+}
+
 // ------------------------------------------------------------------------------------------ A.3
 __global__ void k_posenc(const float* __restrict__ x, float* __restrict__ out, int64_t M, int L) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

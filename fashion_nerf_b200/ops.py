@@ -168,6 +168,20 @@ def adam_step(params: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, e
                                           params.numel(), lr, betas[0], betas[1], eps, step, grad_scale, _stream()), "adam_step")
 
 
+def allreduce_adam_step(peer_grads_dev: int, world: int, offset: int, params: torch.Tensor, exp_avg: torch.Tensor,
+                        exp_avg_sq: torch.Tensor, step: int, *, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+    """Fused mean-all-reduce + Adam over peer memory.  peer_grads_dev: device address of an array of `world` pointers to
+    the ranks' flat gradient buffers (e.g. torch symmetric memory's ``buffer_ptrs_dev``); elements
+    [offset, offset + params.numel()) of every buffer are summed in rank order."""
+    for t in (params, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise _lib.FnerfError("allreduce_adam_step needs contiguous CUDA float32 buffers")
+    with torch.cuda.device(params.device):
+        check(_lib.load().fnerf_allreduce_adam_step(peer_grads_dev, world, offset, params.data_ptr(), exp_avg.data_ptr(),
+                                                    exp_avg_sq.data_ptr(), params.numel(), lr, betas[0], betas[1], eps, step,
+                                                    1.0 / world, _stream()), "allreduce_adam_step")
+
+
 def mlp_tape_bytes(R: int, S: int) -> int:
     return int(_lib.load().fnerf_mlp_tape_bytes(R, S))
 

@@ -62,13 +62,33 @@ class FlatAdam:
 class Trainer:
     """Holds the optimizer state of a NerfModel and runs data-parallel steps."""
 
-    def __init__(self, model: NerfModel, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, group=None):
+    def __init__(self, model: NerfModel, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, group=None,
+                 fused_allreduce: Optional[bool] = None):
+        """fused_allreduce: sum the ranks' gradients with P2P loads over NVLink inside the Adam kernel
+        (``fnerf_allreduce_adam_step`` on a torch symmetric-memory gradient buffer) instead of NCCL all-reduce + Adam.
+        None = use it for 2..4 ranks when the symmetric-memory rendezvous succeeds: the one-shot kernel reads every
+        peer's whole buffer (measured: 32 us vs 50 us for NCCL + Adam at 2 GPUs, 74 us vs 67 us at 8, where NCCL's
+        NVLS / ring schedule moves less data per rank)."""
         self.model, self.group = model, group
         self.n_c, self.n_f = model.coarse.flat.numel(), model.fine.flat.numel()
         self.shared = model.fine is model.coarse
         n = self.n_c if self.shared else self.n_c + self.n_f
         self.opt = FlatAdam(n, model.device, lr, betas, eps)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=model.device)   # the all-reduce buffer
+        self.symm = None
+        self.flat_grad = None
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        if world > 1 and (fused_allreduce or (fused_allreduce is None and world <= 4)) and model.device.type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(n, dtype=torch.float32, device=model.device)
+                self.symm = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                self.flat_grad = buf.zero_()
+            except Exception as e:                     # no P2P / fabric handles: fall back to NCCL
+                if fused_allreduce:
+                    raise
+                self.symm = None
+        if self.flat_grad is None:
+            self.flat_grad = torch.zeros(n, dtype=torch.float32, device=model.device)   # the all-reduce buffer
 
     def step(self, rays_o: torch.Tensor, rays_d: torch.Tensor, target: torch.Tensor, near, far, N_samples: int,
              N_importance: int, cond: Optional[torch.Tensor] = None, *, view_id=None, u_strat=None, u_fine=None,
@@ -90,12 +110,26 @@ class Trainer:
                     g[self.n_c:].copy_(ff.grad)
                 else:
                     g[self.n_c:].zero_()
-            allreduce_mean_(g, self.group)
             m.coarse.flat, m.fine.flat = fc.detach(), ff.detach()
             self.opt.t += 1
-            self.opt.apply(m.coarse.flat, g[:self.n_c], 0)
-            if not self.shared:
-                self.opt.apply(m.fine.flat, g[self.n_c:], self.n_c)
+            if self.symm is not None:
+                # every rank's gradients are in its symmetric buffer: barrier, then each rank sums all peers' buffers over
+                # NVLink inside the Adam kernel (same rank order everywhere -> identical replicas), barrier again so nobody
+                # overwrites its buffer while a peer still reads it
+                from . import ops
+                o = self.opt
+                self.symm.barrier(channel=0)
+                ops.allreduce_adam_step(self.symm.buffer_ptrs_dev, self.symm.world_size, 0, m.coarse.flat, o.m[:self.n_c],
+                                        o.v[:self.n_c], o.t, lr=o.lr, betas=(o.b1, o.b2), eps=o.eps)
+                if not self.shared:
+                    ops.allreduce_adam_step(self.symm.buffer_ptrs_dev, self.symm.world_size, self.n_c, m.fine.flat,
+                                            o.m[self.n_c:], o.v[self.n_c:], o.t, lr=o.lr, betas=(o.b1, o.b2), eps=o.eps)
+                self.symm.barrier(channel=1)
+            else:
+                allreduce_mean_(g, self.group)
+                self.opt.apply(m.coarse.flat, g[:self.n_c], 0)
+                if not self.shared:
+                    self.opt.apply(m.fine.flat, g[self.n_c:], self.n_c)
             m.repack()
         return {"loss": loss.detach(), "psnr": -10.0 * torch.log10(loss_f.detach())}
 

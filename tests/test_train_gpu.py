@@ -409,3 +409,22 @@ def test_checkpoint_model_and_optimizer_round_trip(F, cuda_device, tmp_path):
     l2 = tr2.step(o, d, tgt, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f, precision="fp32")["loss"]
     assert torch.equal(l1, l2)
     assert (model.fine.flat - model2.fine.flat).abs().max() <= 1e-6      # fp32 atomics order in wgrad
+
+
+def test_allreduce_adam_world1_equals_adam(F, cuda_device):
+    """fnerf_allreduce_adam_step with a peer list of one buffer (this rank's) and with the same buffer listed three
+    times (sum of three = 3 g, scaled by 1/3) reproduces fnerf_adam_step; offsets address a slice of the buffers."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(12)
+    n, off = 50_001, 1234
+    grad = torch.randn(off + n, generator=g).to(dev)
+    for world in (1, 3):
+        p_ref = torch.randn(n, generator=torch.Generator().manual_seed(13)).to(dev)
+        p_got = p_ref.clone()
+        m1, v1, m2, v2 = (torch.zeros(n, device=dev) for _ in range(4))
+        ptrs = torch.tensor([grad.data_ptr()] * world, dtype=torch.int64, device=dev)
+        for t in (1, 2):
+            F.ops.adam_step(p_ref, grad[off:].contiguous(), m1, v1, t)
+            F.ops.allreduce_adam_step(ptrs.data_ptr(), world, off, p_got, m2, v2, t)
+        tol = 0 if world == 1 else 1e-6
+        assert (p_ref - p_got).abs().max() <= tol
