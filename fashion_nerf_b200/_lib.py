@@ -65,6 +65,7 @@ SIGNATURES = {
                                 ctypes.c_float, ctypes.c_float, c_int64, ctypes.c_float, c_void_p]),
     "fnerf_allreduce_adam_step": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float,
                                           ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int64, ctypes.c_float, c_void_p]),
+    "fnerf_multimem_allreduce": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p]),
     "fnerf_mlp_tape_bytes": (c_int64, [c_int64, c_int64]),
     "fnerf_mlp_fwd_tape": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),

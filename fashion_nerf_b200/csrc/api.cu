@@ -176,6 +176,15 @@ int fnerf_allreduce_adam_step(const float* const* peer_grads, int world, int64_t
                                (cudaStream_t)stream);
 }
 
+int fnerf_multimem_allreduce(float* multicast_ptr, int rank, int world, int64_t n, fnerf_stream_t stream) {
+  FN_REQUIRE(n >= 0 && (n & 3) == 0, FNERF_ERR_SIZE, "multimem_allreduce: n=%lld must be a multiple of 4", (long long)n);
+  FN_REQUIRE(world >= 1 && rank >= 0 && rank < world, FNERF_ERR_SIZE, "multimem_allreduce: bad rank %d / world %d", rank, world);
+  if (n == 0) return 0;
+  FN_REQUIRE(multicast_ptr != nullptr, FNERF_ERR_NULL, "multimem_allreduce: null multicast pointer");
+  FN_REQUIRE(FN_ALIGNED16(multicast_ptr), FNERF_ERR_ALIGN, "multimem_allreduce: pointer must be 16-byte aligned");
+  return launch_multimem_allreduce(multicast_ptr, rank, world, n, (cudaStream_t)stream);
+}
+
 int64_t fnerf_mlp_tape_bytes(int64_t R, int64_t S) { return mlp_tape_bytes(R * S); }
 int64_t fnerf_mlp_bwd_tape_workspace_bytes(int64_t R, int64_t S) { return mlp_bwd_from_tape_workspace_bytes(R * S); }
 

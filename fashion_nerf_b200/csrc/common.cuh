@@ -53,6 +53,7 @@ int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s);
 int launch_unpack(const void* packed, float* flat, int cond, cudaStream_t s);
 int launch_allreduce_adam(const float* const* peer_grads, int world, int64_t offset, float* p, float* m, float* v, int64_t n, float lr,
                           float b1, float b2, float eps, int64_t t, float grad_scale, cudaStream_t s);
+int launch_multimem_allreduce(float* mc, int rank, int world, int64_t n, cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int64_t t,
                 float grad_scale, cudaStream_t s);
 int launch_cond_project(const void* packed, const float* cond, float* proj, int64_t C, cudaStream_t s);

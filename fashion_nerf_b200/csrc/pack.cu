@@ -185,6 +185,43 @@ int launch_allreduce_adam(const float* const* peer_grads, int world, int64_t off
   return check_launch("allreduce_adam_step");
 }
 
+// In-place sum of the ranks' gradient buffers through an NVSwitch multicast mapping (NVLS): rank r owns every world-th
+// 16-byte group, pulls the switch-reduced sum of that group (multimem.ld_reduce: the switch adds the `world` copies) and
+// multicast-stores it back to all ranks.  One reducer per element -> every rank ends up with identical bits.
+__global__ void __launch_bounds__(256) k_multimem_allreduce(float* __restrict__ mc, int rank, int world, int64_t n4) {
+  // this rank's groups: i = j * world + rank; four of them in flight per thread (the switch round trip is long)
+  const int64_t mine = (n4 - rank + world - 1) / world;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < mine; j0 += 4 * stride) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = j0 + u * stride;
+      if (j < mine)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[u][0]), "=f"(v[u][1]), "=f"(v[u][2]), "=f"(v[u][3]) : "l"(mc + 4 * (j * world + rank)) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = j0 + u * stride;
+      if (j < mine)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(mc + 4 * (j * world + rank)), "f"(v[u][0]), "f"(v[u][1]), "f"(v[u][2]), "f"(v[u][3]) : "memory");
+    }
+  }
+}
+
+int launch_multimem_allreduce(float* mc, int rank, int world, int64_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 / world / 4 + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_multimem_allreduce<<<(unsigned)blocks, 256, 0, s>>>(mc, rank, world, n4);
+  return check_launch("multimem_allreduce");
+}
+
 // ------------------------------------------------------------------------------------------ A.3
 __global__ void k_posenc(const float* __restrict__ x, float* __restrict__ out, int64_t M, int L) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

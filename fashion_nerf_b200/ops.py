@@ -182,6 +182,12 @@ def allreduce_adam_step(peer_grads_dev: int, world: int, offset: int, params: to
                                                     1.0 / world, _stream()), "allreduce_adam_step")
 
 
+def multimem_allreduce(multicast_ptr: int, rank: int, world: int, n: int, device) -> None:
+    """In-place sum over the ranks' buffers behind an NVSwitch multicast mapping (NVLS); n % 4 == 0."""
+    with torch.cuda.device(device):
+        check(_lib.load().fnerf_multimem_allreduce(multicast_ptr, rank, world, n, _stream()), "multimem_allreduce")
+
+
 def mlp_tape_bytes(R: int, S: int) -> int:
     return int(_lib.load().fnerf_mlp_tape_bytes(R, S))
 

@@ -13,7 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--precision", default="bf16")
-ap.add_argument("--allreduce", default="auto", choices=["auto", "fused", "nccl"])
+ap.add_argument("--allreduce", default="auto", choices=["auto", "fused", "nvls", "nccl"])
 args = ap.parse_args()
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(local)
@@ -27,7 +27,7 @@ o, d = o_all[idx].to(dev), d_all[idx].to(dev)
 tgt = torch.rand(4096, 3, generator=torch.Generator().manual_seed(100 + rank)).to(dev)
 g = torch.Generator().manual_seed(rank)
 u_s, u_f = torch.rand(4096, 64, generator=g).to(dev), torch.rand(4096, 128, generator=g).to(dev)
-tr = Trainer(model, fused_allreduce={"auto": None, "fused": True, "nccl": False}[args.allreduce])
+tr = Trainer(model, fused_allreduce={"auto": None, "fused": True, "nvls": "nvls", "nccl": False}[args.allreduce])
 times, losses = [], []
 for i in range(args.warmup + args.steps):
     if world > 1:
@@ -61,7 +61,7 @@ if rank == 0:
                       "Mrays_per_s": world * 4096 / ms / 1e3, "algorithmic_TFLOPs_per_gpu": flop / ms / 1e9,
                       "precision_fwd": args.precision, "bwd": "bf16 tcgen05 (tape + dgrad + wgrad)" if args.precision == "bf16" else "fp32 SGEMM chain", "loss_first_last": [losses[0], losses[-1]],
                       "replicas_identical": same,
-                      "allreduce": "fused P2P all-reduce + Adam (symmetric memory)" if tr.symm is not None else ("NCCL" if world > 1 else "none"),
+                      "allreduce": ("NVLS multimem all-reduce + Adam" if tr.nvls else "fused P2P all-reduce + Adam (symmetric memory)") if tr.symm is not None else ("NCCL" if world > 1 else "none"),
                       "param_checksum": model.coarse.flat.double().sum().item()}))
 if world > 1:
     dist.barrier()

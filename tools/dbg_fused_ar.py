@@ -23,6 +23,23 @@ t_bar = timeit(lambda: h.barrier(channel=0))
 t_k = timeit(lambda: F.ops.allreduce_adam_step(h.buffer_ptrs_dev, world, 0, p, m, v, 1))
 t_all = timeit(lambda: (h.barrier(channel=0), F.ops.allreduce_adam_step(h.buffer_ptrs_dev, world, 0, p, m, v, 1), h.barrier(channel=1)))
 t_nccl = timeit(lambda: (dist.all_reduce(g2), g2.div_(world), F.ops.adam_step(p, g2, m, v, 1)))
+# NVLS two-shot: correctness against NCCL, then timing
+t_mm = -1.0
+mc = h.multicast_ptr
+if mc:
+    n4 = n // 4 * 4
+    buf.copy_(torch.randn(n, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank)))
+    ref = buf.clone(); dist.all_reduce(ref)
+    h.barrier(channel=0)
+    F.ops.multimem_allreduce(mc, rank, world, n4, dev)
+    h.barrier(channel=1)
+    torch.cuda.synchronize()
+    err = (buf[:n4] - ref[:n4]).abs().max().item()
+    chk = buf[:n4].double().sum().reshape(1); allc = [torch.empty_like(chk) for _ in range(world)]; dist.all_gather(allc, chk)
+    same = all(torch.equal(allc[0], c) for c in allc)
+    t_mm = timeit(lambda: (h.barrier(channel=0), F.ops.multimem_allreduce(mc, rank, world, n4, dev), h.barrier(channel=1),
+                           F.ops.adam_step(p, buf, m, v, 1, grad_scale=1.0 / world)))
+    if rank == 0: print(f"multimem: max |err| vs NCCL {err:.3e}, identical on all ranks {same}, barrier+NVLS+barrier+adam {t_mm:.1f} us")
 if rank == 0:
-    print(f"world {world}: symm barrier {t_bar:.1f} us | fused kernel {t_k:.1f} us | barrier+kernel+barrier {t_all:.1f} us | NCCL all_reduce + div + adam {t_nccl:.1f} us | multicast {h.has_multicast_support}")
+    print(f"world {world}: symm barrier {t_bar:.1f} us | fused kernel {t_k:.1f} us | barrier+kernel+barrier {t_all:.1f} us | NCCL all_reduce + div + adam {t_nccl:.1f} us | multicast ptr {hex(mc) if mc else 0}")
 dist.destroy_process_group()
