@@ -41,7 +41,7 @@ FLOP_PER_RAY = FLOP_PER_SAMPLE * (N_C + N_C + N_F)
 # dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass k_mlp_tc launch of THIS workload (640,000 rays x 192
 # samples) from one `ncu --set full` capture of `bench.py --steps 1 --warmup 3` (profiles/r1_bench_fine_launch_ncu_key_metrics.txt);
 # the algorithmic HBM bytes of that launch are 20 B/sample = 2,457,600,000
-NCU_FINE_LAUNCH_DRAM_BYTES = 538_791_424 + 1_917_652_000
+NCU_FINE_LAUNCH_DRAM_BYTES = 542_652_160 + 1_917_181_000
 CPU_SAMPLE_RAYS = 4096
 WORKLOAD = ("single-B200 full-frame 800x800 render per GPU (BASELINE configs[1]); view r of N per rank, "
             "random-init 8x256 NeRF MLPs (seeds 0/1), L=10/4 PE")
