@@ -505,7 +505,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
             const uint32_t src = base + kOffAct + kb * kKBlockBytes + off;
             uint8_t* dstg = tape_tile + (size_t)(kTapeSlotH + 4 * step + (int)kb) * kKBlockBytes + off;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dstg + i * 512) = ld_shared_v4(src + i * 512);
+            for (int i = 0; i < 4; ++i) {       // streaming (evict-first) stores: the tape is next read by wgrad, gigabytes later
+              const uint4 t4 = ld_shared_v4(src + i * 512);
+              asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dstg + i * 512), "r"(t4.x), "r"(t4.y), "r"(t4.z), "r"(t4.w) : "memory");
+            }
           }
           FN_TRACE(wtile == 2 && row == 0, wslot++);
         }
