@@ -563,7 +563,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           c1 = brgb[1] + ((c1 + p1.y) + (p2.y + p3.y));
           c2 = brgb[2] + ((c2 + p1.z) + (p2.z + p3.z));
           const float sg = heads_s[kAuxBAlpha - kAuxWAlpha] + ((sigma + p1.w) + (p2.w + p3.w));
-          if (g < P.M) P.raw[g] = make_float4(c0, c1, c2, sg);
+          // streaming store: raw is gigabytes per frame, read once by compositing
+          if (g < P.M) asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.raw + g), "f"(c0), "f"(c1), "f"(c2), "f"(sg) : "memory");
         }
       }
       ++wtile;
