@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FNERF_LIB") or os.path.join(HERE, "libfnerf.so")   # FNERF_LIB: A/B builds (tools/)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 
@@ -27,11 +27,13 @@ class RenderArgs(ctypes.Structure):
         ("rays_o", c_void_p), ("rays_d", c_void_p), ("near", c_void_p), ("far", c_void_p),
         ("t_vals", c_void_p), ("u_strat", c_void_p), ("u_fine", c_void_p),
         ("u_fine_row_stride", c_int64),
+        ("raw_noise_coarse", c_void_p), ("raw_noise_fine", c_void_p),
         ("cond_proj_coarse", c_void_p), ("cond_proj_fine", c_void_p), ("cond_index", c_void_p),
         ("C", c_int64), ("R", c_int64), ("Nc", c_int64), ("Nf", c_int64),
         ("white_bkgd", c_int), ("lindisp", c_int),
         ("rgb", c_void_p), ("disp", c_void_p), ("acc", c_void_p), ("depth", c_void_p),
         ("rgb0", c_void_p), ("disp0", c_void_p), ("acc0", c_void_p), ("z_std", c_void_p),
+        ("depth0", c_void_p),
         ("z_c", c_void_p), ("z_f", c_void_p), ("raw_c", c_void_p), ("raw_f", c_void_p),
         ("weights_c", c_void_p), ("weights_f", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
@@ -58,7 +60,7 @@ SIGNATURES = {
     "fnerf_cond_project": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "fnerf_mlp_fwd": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int64, c_void_p, c_int64, c_int64, c_void_p]),
-    "fnerf_mlp_bwd_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "fnerf_mlp_bwd_workspace_bytes": (c_int64, [c_int, c_int, c_int64, c_int64]),
     "fnerf_mlp_bwd": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "fnerf_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_float, ctypes.c_float,
@@ -74,10 +76,11 @@ SIGNATURES = {
                                    c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "fnerf_composite_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_int, c_void_p]),
-    "fnerf_composite_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "fnerf_composite_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int, c_void_p]),
     "fnerf_render_rays_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "fnerf_render_rays": (c_int, [ctypes.POINTER(RenderArgs), c_void_p]),
+    "fnerf_debug_wgrad_tc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int, c_int64, c_void_p]),
 }
 
 _lib = None

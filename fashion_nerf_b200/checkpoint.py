@@ -5,7 +5,11 @@ use_viewdirs=True)` module unchanged.
     {"global_step": int,
      "network_fn_state_dict":   {pts_linears.{0..7}.weight/bias, views_linears.0.*, feature_linear.*, alpha_linear.*, rgb_linear.*},
      "network_fine_state_dict": same keys (absent when coarse and fine share one network),
-     "optimizer_state_dict":    {"step", "exp_avg", "exp_avg_sq"} over the flat parameter layout (this package's Adam)}
+     "optimizer_state_dict":    {"step", "exp_avg", "exp_avg_sq", "lr", "betas", "eps"} over the flat parameter layout
+                                (this package's Adam).  A canonical torch.optim.Adam state dict ({"state", "param_groups"}
+                                over list(model.parameters()) + list(model_fine.parameters())) is recognised on load and
+                                converted; checkpoints WRITTEN here carry the flat form, so only the network
+                                dictionaries are loadable by the canonical code unchanged.}
 
 Conditioned networks (A.8) differ only in `pts_linears.5.weight` being [256, 63+256+256]; `cond` is inferred
 from that shape on load.  Everything here is host-side dictionary work and runs without a GPU; only
@@ -108,17 +112,63 @@ def load_model(path_or_dict, device) -> Tuple[NerfModel, dict]:
     return NerfModel(coarse, fine), ck
 
 
-def restore_optimizer(trainer, ck: dict) -> None:
-    """Puts a checkpoint's Adam moments / step count back into a train.Trainer."""
+# parameter order of the canonical module (its __init__ declares pts_linears, views_linears, feature_linear,
+# alpha_linear, rgb_linear): torch.optim.Adam numbers its state by position in list(model.parameters())
+_MODULE_ORDER = [f"pts_linears.{i}" for i in range(8)] + ["views_linears.0", "feature_linear", "alpha_linear", "rgb_linear"]
+
+
+def convert_torch_adam_state(opt_sd: dict, cond: bool, two_networks: bool) -> dict:
+    """torch.optim.Adam.state_dict() of Adam(list(coarse.parameters()) + list(fine.parameters())) -> the flat form."""
+    state, groups = opt_sd["state"], opt_sd["param_groups"]
+    names = [n + sfx for n in _MODULE_ORDER for sfx in (".weight", ".bias")]
+    shapes = param_shapes(cond)
+    n_nets = 2 if two_networks else 1
+    order = [pid for g in groups for pid in g["params"]]
+    if len(order) != n_nets * len(names):
+        raise ValueError(f"torch Adam state covers {len(order)} tensors, expected {n_nets * len(names)} "
+                         f"({n_nets} network(s) x {len(names)} parameters)")
+    nets, step = [], 0
+    for k in range(n_nets):
+        avg, sq = {}, {}
+        for j, name in enumerate(names):
+            st = state.get(order[k * len(names) + j])
+            if st is None:                                   # parameter never stepped: zero moments
+                avg[name], sq[name] = torch.zeros(shapes[name]), torch.zeros(shapes[name])
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(shapes[name]):
+                raise ValueError(f"torch Adam state: {name} has shape {tuple(st['exp_avg'].shape)} != {tuple(shapes[name])}")
+            avg[name], sq[name] = st["exp_avg"].detach().float().cpu(), st["exp_avg_sq"].detach().float().cpu()
+            step = max(step, int(st["step"]))
+        nets.append((flatten_state_dict(avg, cond), flatten_state_dict(sq, cond)))
+    g0 = groups[0]
+    return {"step": step, "exp_avg": torch.cat([a for a, _ in nets]), "exp_avg_sq": torch.cat([b for _, b in nets]),
+            "lr": float(g0["lr"]), "betas": tuple(g0["betas"]), "eps": float(g0["eps"])}
+
+
+def restore_optimizer(trainer, ck: dict, *, restore_hyperparameters: bool = True) -> None:
+    """Puts a checkpoint's Adam moments / step count (and lr / betas / eps when recorded) back into a train.Trainer.
+    Accepts this package's flat form and a canonical torch.optim.Adam state dict."""
     st = ck.get("optimizer")
     if st is None:
         return
-    if st["exp_avg"].numel() != trainer.opt.m.numel():
+    if "state" in st and "param_groups" in st:
+        st = convert_torch_adam_state(st, ck["cond"], ck["fine"] is not None)
+    for k in ("step", "exp_avg", "exp_avg_sq"):
+        if k not in st:
+            raise ValueError(f"optimizer_state_dict has no '{k}': neither this package's flat Adam state nor a torch.optim.Adam one")
+    if st["exp_avg"].numel() != trainer.opt.m.numel() or st["exp_avg_sq"].numel() != trainer.opt.v.numel():
         raise ValueError("optimizer state does not match the model's parameter count")
     trainer.opt.m.copy_(st["exp_avg"])
     trainer.opt.v.copy_(st["exp_avg_sq"])
     trainer.opt.t = int(st["step"])
+    if restore_hyperparameters:
+        if "lr" in st:
+            trainer.opt.lr = float(st["lr"])
+        if "betas" in st:
+            trainer.opt.b1, trainer.opt.b2 = (float(b) for b in st["betas"])
+        if "eps" in st:
+            trainer.opt.eps = float(st["eps"])
 
 
 __all__ = ["save_checkpoint", "read_checkpoint", "load_model", "make_checkpoint", "validate_state_dict", "infer_cond",
-           "restore_optimizer", "flatten_state_dict", "unflatten"]
+           "restore_optimizer", "convert_torch_adam_state", "flatten_state_dict", "unflatten"]

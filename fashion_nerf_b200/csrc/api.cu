@@ -135,9 +135,12 @@ int fnerf_mlp_fwd(int precision, const void* packed, int cond, const float* rays
                                            : launch_mlp_fp32(a, (cudaStream_t)stream);
 }
 
-int64_t fnerf_mlp_bwd_workspace_bytes(int64_t R, int64_t S) {
-  const int64_t a = mlp_bwd_workspace_bytes(R, S), b = mlp_bwd_tc_workspace_bytes(R * S);   // fp32 chain / bf16 tape
-  return a > b ? a : b;
+// the path fnerf_mlp_bwd takes for (precision, cond): bf16 tape + tcgen05 backward, or the fp32 SGEMM chain
+static bool bwd_uses_tc(int precision, int cond) { return precision == FNERF_PRECISION_BF16 && !cond; }
+
+int64_t fnerf_mlp_bwd_workspace_bytes(int precision, int cond, int64_t R, int64_t S) {
+  if (R < 0 || S < 1) return -1;
+  return bwd_uses_tc(precision, cond) ? mlp_bwd_tc_workspace_bytes(R, S) : mlp_bwd_workspace_bytes(R, S);
 }
 
 int fnerf_mlp_bwd(int precision, const void* packed, int cond, const float* rays_o, const float* rays_d,
@@ -147,12 +150,12 @@ int fnerf_mlp_bwd(int precision, const void* packed, int cond, const float* rays
   int rc = validate_mlp("mlp_bwd", precision, packed, cond, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, g_raw, R, S);
   if (rc != 0 || R == 0) return rc;
   FN_REQUIRE(flat_grad && workspace, FNERF_ERR_NULL, "mlp_bwd: null pointer");
-  FN_REQUIRE(workspace_bytes >= fnerf_mlp_bwd_workspace_bytes(R, S), FNERF_ERR_WORKSPACE, "mlp_bwd: workspace too small");
+  FN_REQUIRE(workspace_bytes >= fnerf_mlp_bwd_workspace_bytes(precision, cond, R, S), FNERF_ERR_WORKSPACE, "mlp_bwd: workspace too small");
   FN_REQUIRE(FN_ALIGNED16(workspace) && FN_ALIGNED16(g_raw), FNERF_ERR_ALIGN, "mlp_bwd: workspace / g_raw must be 16-byte aligned");
   MlpArgs a{packed, cond ? 1 : 0, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, nullptr, R, S};
   // bf16: forward with tape + tcgen05 dgrad chain + tcgen05 wgrad (unconditioned networks); the conditioned
   // variant and FNERF_PRECISION_FP32 take the fp32 SGEMM chain
-  if (precision == FNERF_PRECISION_BF16 && !cond)
+  if (bwd_uses_tc(precision, cond))
     return launch_mlp_bwd_tc(a, g_raw, flat_grad, workspace, workspace_bytes, (cudaStream_t)stream);
   return launch_mlp_bwd_fp32(a, g_raw, flat_grad, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -230,14 +233,14 @@ int fnerf_composite_fwd(const float* raw, const float* z, const float* dnorm, co
                               (cudaStream_t)stream);
 }
 
-int fnerf_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* g_rgb,
+int fnerf_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* raw_noise, const float* g_rgb,
                         const float* g_depth, const float* g_acc, float* g_raw, int64_t R, int64_t S,
                         int white_bkgd, fnerf_stream_t stream) {
   FN_REQUIRE(R >= 0 && S >= 1 && S <= 4096, FNERF_ERR_SIZE, "composite_bwd: bad R=%lld S=%lld", (long long)R, (long long)S);
   if (R == 0) return 0;
   FN_REQUIRE(raw && z && dnorm && g_rgb && g_raw, FNERF_ERR_NULL, "composite_bwd: null pointer");
   FN_REQUIRE(FN_ALIGNED16(raw) && FN_ALIGNED16(g_raw), FNERF_ERR_ALIGN, "composite_bwd: raw/g_raw must be 16-byte aligned");
-  return launch_composite_bwd(raw, z, dnorm, g_rgb, g_depth, g_acc, g_raw, R, S, white_bkgd, (cudaStream_t)stream);
+  return launch_composite_bwd(raw, z, dnorm, raw_noise, g_rgb, g_depth, g_acc, g_raw, R, S, white_bkgd, (cudaStream_t)stream);
 }
 
 int64_t fnerf_render_rays_workspace_bytes(int64_t R, int64_t Nc, int64_t Nf) {
@@ -274,40 +277,49 @@ int fnerf_render_rays(const fnerf_render_args* a, fnerf_stream_t stream) {
   float* z_samples = f(L.z_samples);
   float* z_f = a->z_f ? a->z_f : f(L.z_f);
   float* raw_f = a->raw_f ? a->raw_f : f(L.raw_f);
-  float* depth0 = f(L.depth0);
+  float* depth0 = a->depth0 ? a->depth0 : f(L.depth0);
   FN_REQUIRE(FN_ALIGNED16(raw_c) && FN_ALIGNED16(raw_f), FNERF_ERR_ALIGN, "render_rays: raw taps must be 16-byte aligned");
 
   int rc;
+  auto record = [&](void* ev) -> int {            // optional profiling events: a failed record is an error, not a silent gap
+    if (ev == nullptr) return 0;
+    cudaError_t e = cudaEventRecord((cudaEvent_t)ev, s);
+    return e == cudaSuccess ? 0 : set_error((int)e, "render_rays: cudaEventRecord: %s", cudaGetErrorString(e));
+  };
+  auto d2d = [&](float* dst, const float* src, int64_t floats) -> int {
+    cudaError_t e = cudaMemcpyAsync(dst, src, floats * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    return e == cudaSuccess ? 0 : set_error((int)e, "render_rays: cudaMemcpyAsync: %s", cudaGetErrorString(e));
+  };
   if ((rc = fnerf_ray_setup(a->rays_d, viewdirs, dnorm, R, stream))) return rc;
   if ((rc = fnerf_stratified(a->near, a->far, a->t_vals, a->u_strat, z_c, R, Nc, a->lindisp, stream))) return rc;
-  if (a->ev_coarse_start) cudaEventRecord((cudaEvent_t)a->ev_coarse_start, s);
+  if ((rc = record(a->ev_coarse_start))) return rc;
   if (a->tape_coarse) {
     if ((rc = fnerf_mlp_fwd_tape(a->packed_coarse, a->cond, a->rays_o, a->rays_d, viewdirs, z_c, a->cond_proj_coarse,
                                  a->cond_index, a->C, raw_c, a->tape_coarse, a->tape_coarse_bytes, R, Nc, stream))) return rc;
   } else if ((rc = fnerf_mlp_fwd(a->precision, a->packed_coarse, a->cond, a->rays_o, a->rays_d, viewdirs, z_c,
                                  a->cond_proj_coarse, a->cond_index, a->C, raw_c, R, Nc, stream))) return rc;
-  if (a->ev_coarse_stop) cudaEventRecord((cudaEvent_t)a->ev_coarse_stop, s);
+  if ((rc = record(a->ev_coarse_stop))) return rc;
   if (Nf == 0) {
-    if ((rc = fnerf_composite_fwd(raw_c, z_c, dnorm, nullptr, a->rgb, a->depth, a->acc, a->disp, a->weights_c ? weights_c : nullptr,
-                                  R, Nc, a->white_bkgd, stream))) return rc;
-    cudaMemcpyAsync(a->rgb0, a->rgb, R * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
-    cudaMemcpyAsync(a->disp0, a->disp, R * sizeof(float), cudaMemcpyDeviceToDevice, s);
-    cudaMemcpyAsync(a->acc0, a->acc, R * sizeof(float), cudaMemcpyDeviceToDevice, s);
-    cudaMemsetAsync(a->z_std, 0, R * sizeof(float), s);
+    if ((rc = fnerf_composite_fwd(raw_c, z_c, dnorm, a->raw_noise_coarse, a->rgb, a->depth, a->acc, a->disp,
+                                  a->weights_c ? weights_c : nullptr, R, Nc, a->white_bkgd, stream))) return rc;
+    if ((rc = d2d(a->rgb0, a->rgb, R * 3)) || (rc = d2d(a->disp0, a->disp, R)) || (rc = d2d(a->acc0, a->acc, R))) return rc;
+    if (a->depth0 && (rc = d2d(a->depth0, a->depth, R))) return rc;
+    if (cudaError_t e = cudaMemsetAsync(a->z_std, 0, R * sizeof(float), s))
+      return set_error((int)e, "render_rays: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return check_launch("render_rays");
   }
-  if ((rc = fnerf_composite_fwd(raw_c, z_c, dnorm, nullptr, a->rgb0, depth0, a->acc0, a->disp0, weights_c, R, Nc,
+  if ((rc = fnerf_composite_fwd(raw_c, z_c, dnorm, a->raw_noise_coarse, a->rgb0, depth0, a->acc0, a->disp0, weights_c, R, Nc,
                                 a->white_bkgd, stream))) return rc;
   if ((rc = fnerf_importance(z_c, weights_c, a->u_fine, a->u_fine_row_stride, z_samples, z_f, nullptr, a->z_std,
                              R, Nc, Nf, stream))) return rc;
-  if (a->ev_fine_start) cudaEventRecord((cudaEvent_t)a->ev_fine_start, s);
+  if ((rc = record(a->ev_fine_start))) return rc;
   if (a->tape_fine) {
     if ((rc = fnerf_mlp_fwd_tape(a->packed_fine, a->cond, a->rays_o, a->rays_d, viewdirs, z_f, a->cond_proj_fine,
                                  a->cond_index, a->C, raw_f, a->tape_fine, a->tape_fine_bytes, R, Nc + Nf, stream))) return rc;
   } else if ((rc = fnerf_mlp_fwd(a->precision, a->packed_fine, a->cond, a->rays_o, a->rays_d, viewdirs, z_f,
                                  a->cond_proj_fine, a->cond_index, a->C, raw_f, R, Nc + Nf, stream))) return rc;
-  if (a->ev_fine_stop) cudaEventRecord((cudaEvent_t)a->ev_fine_stop, s);
-  if ((rc = fnerf_composite_fwd(raw_f, z_f, dnorm, nullptr, a->rgb, a->depth, a->acc, a->disp, a->weights_f, R,
+  if ((rc = record(a->ev_fine_stop))) return rc;
+  if ((rc = fnerf_composite_fwd(raw_f, z_f, dnorm, a->raw_noise_fine, a->rgb, a->depth, a->acc, a->disp, a->weights_f, R,
                                 Nc + Nf, a->white_bkgd, stream))) return rc;
   return 0;
 }

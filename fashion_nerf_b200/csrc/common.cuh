@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include "../../include/fnerf.h"
 #include "layout.h"
 
@@ -22,16 +23,41 @@ inline int check_launch(const char* what) {
   do { if (!(cond)) return ::fnerf::set_error((code), __VA_ARGS__); } while (0)
 #define FN_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)
 
-inline int num_sms() {
-  static int sms[64] = {0};
+// One-time, per-device initialisation (cudaFuncSetAttribute, occupancy queries, device properties) guarded by
+// std::call_once, as SURVEY.md 8(b) prescribes: the entry points are re-entrant and may be called from several
+// host threads on different streams.  The callable's cudaError_t is kept and returned on every later call.
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+  std::once_flag flag[kMaxDevices];
+  cudaError_t err[kMaxDevices];
+};
+inline int current_device() {
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (sms[dev] == 0) {
+  return (dev < 0 || dev >= kMaxDevices) ? 0 : dev;
+}
+template <class F>
+inline cudaError_t device_once(DeviceOnce& o, F&& f) {
+  const int dev = current_device();
+  std::call_once(o.flag[dev], [&] { o.err[dev] = f(); });
+  return o.err[dev];
+}
+// kernels that need more than 48 KB of dynamic shared memory opt in once per device
+template <class K>
+inline cudaError_t opt_in_smem_once(DeviceOnce& o, K kernel, size_t bytes) {
+  return device_once(o, [&] { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); });
+}
+
+inline int num_sms() {
+  static DeviceOnce once;
+  static int sms[kMaxDevices];
+  const int dev = current_device();
+  device_once(once, [&] {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
     sms[dev] = v;
-  }
+    return cudaSuccess;
+  });
   return sms[dev];
 }
 
@@ -46,7 +72,7 @@ int launch_posenc(const float* x, float* out, int64_t M, int L, cudaStream_t s);
 int launch_composite_fwd(const float* raw, const float* z, const float* dnorm, const float* noise,
                          float* rgb, float* depth, float* acc, float* disp, float* weights,
                          int64_t R, int64_t S, int white, cudaStream_t s);
-int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* g_rgb,
+int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* noise, const float* g_rgb,
                          const float* g_depth, const float* g_acc, float* g_raw, int64_t R,
                          int64_t S, int white, cudaStream_t s);
 int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s);
@@ -69,7 +95,7 @@ int launch_mlp_tc(const MlpArgs& a, cudaStream_t s);
 int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cudaStream_t s);   // training forward: also writes the tape
 
 int64_t mlp_bwd_workspace_bytes(int64_t R, int64_t S);
-int64_t mlp_bwd_tc_workspace_bytes(int64_t M);
+int64_t mlp_bwd_tc_workspace_bytes(int64_t R, int64_t S);
 int64_t mlp_tape_bytes(int64_t M);                       // forward tape of one bf16 network query
 int64_t mlp_bwd_from_tape_workspace_bytes(int64_t M);
 int launch_mlp_fwd_tape(const MlpArgs& a, void* tape, cudaStream_t s);

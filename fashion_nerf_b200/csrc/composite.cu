@@ -118,7 +118,7 @@ k_composite_fwd(const float4* __restrict__ raw, const float* __restrict__ z,
 template <int NB>
 __global__ void __launch_bounds__(kCompWarps * 32)
 k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
-                    const float* __restrict__ dnorm, float* __restrict__ rgb_out,
+                    const float* __restrict__ dnorm, const float* __restrict__ noise, float* __restrict__ rgb_out,
                     float* __restrict__ depth_out, float* __restrict__ acc_out,
                     float* __restrict__ disp_out, float* __restrict__ weights, int64_t R, int S, int white) {
   const int lane = threadIdx.x & 31;
@@ -134,7 +134,10 @@ k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
       const int i = b * 32 + lane;
       rv[b] = make_float4(0.f, 0.f, 0.f, 0.f);
       zv[b] = 0.f;
-      if (i < S) { rv[b] = ldg_stream4(rawr + i); zv[b] = ldg_stream(zr + i); }
+      if (i < S) {
+        rv[b] = ldg_stream4(rawr + i); zv[b] = ldg_stream(zr + i);
+        if (noise != nullptr) rv[b].w += ldg_stream(noise + r * S + i);     // sigma = raw[...,3] + raw_noise (A.5)
+      }
     }
     const float dn = dnorm[r];
     float carry = 1.0f, a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
@@ -191,15 +194,15 @@ int launch_composite_fwd(const float* raw, const float* z, const float* dnorm, c
   int64_t blocks = (R + kCompWarps - 1) / kCompWarps;
   const int64_t cap = (int64_t)num_sms() * 8 * 4;   // 8 resident CTAs/SM x 4 waves, grid-stride beyond
   if (blocks > cap) blocks = cap;
-  if (noise == nullptr && S <= 256) {
+  if (S <= 256) {
     const float4* raw4 = (const float4*)raw;
     const unsigned g = (unsigned)blocks, t = kCompWarps * 32;
     switch ((S + 31) / 32) {
-      case 1: k_composite_fwd_reg<1><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
-      case 2: k_composite_fwd_reg<2><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
-      case 3: case 4: k_composite_fwd_reg<4><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
-      case 5: case 6: k_composite_fwd_reg<6><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
-      default: k_composite_fwd_reg<8><<<g, t, 0, s>>>(raw4, z, dnorm, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      case 1: k_composite_fwd_reg<1><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      case 2: k_composite_fwd_reg<2><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      case 3: case 4: k_composite_fwd_reg<4><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      case 5: case 6: k_composite_fwd_reg<6><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      default: k_composite_fwd_reg<8><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
     }
     return check_launch("composite_fwd");
   }
@@ -221,7 +224,7 @@ constexpr int kBwdWarps = 4;
 
 __global__ void __launch_bounds__(kBwdWarps * 32)
 k_composite_bwd(const float4* __restrict__ raw, const float* __restrict__ z,
-                const float* __restrict__ dnorm, const float* __restrict__ g_rgb,
+                const float* __restrict__ dnorm, const float* __restrict__ noise, const float* __restrict__ g_rgb,
                 const float* __restrict__ g_depth, const float* __restrict__ g_acc,
                 float4* __restrict__ g_raw, int64_t R, int S, int white) {
   extern __shared__ float smem[];
@@ -244,6 +247,7 @@ k_composite_bwd(const float4* __restrict__ raw, const float* __restrict__ z,
       const int i = b * 32 + lane;
       const bool valid = i < S;
       float4 rv = valid ? rawr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && noise != nullptr) rv.w += noise[r * S + i];
       const float zv = valid ? zr[i] : 0.f;
       const float z_up = (i + 1 < S) ? zr[i + 1] : 0.f;
       float dist = (i == S - 1) ? 1e10f : (z_up - zv);
@@ -282,7 +286,8 @@ k_composite_bwd(const float4* __restrict__ raw, const float* __restrict__ z,
       const float suffix = (q - wv) + tail;   // exclusive
       tail += __shfl_sync(0xffffffffu, q, 0);
       if (valid) {
-        const float4 rv = rawr[i];
+        float4 rv = rawr[i];
+        if (noise != nullptr) rv.w += noise[r * S + i];
         const float zv = zr[i];
         const float z_up = (i + 1 < S) ? zr[i + 1] : 0.f;
         float dist = (i == S - 1) ? 1e10f : (z_up - zv);
@@ -309,7 +314,7 @@ k_composite_bwd(const float4* __restrict__ raw, const float* __restrict__ z,
 template <int NB>
 __global__ void __launch_bounds__(kCompWarps * 32)
 k_composite_bwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
-                    const float* __restrict__ dnorm, const float* __restrict__ g_rgb,
+                    const float* __restrict__ dnorm, const float* __restrict__ noise, const float* __restrict__ g_rgb,
                     const float* __restrict__ g_depth, const float* __restrict__ g_acc,
                     float4* __restrict__ g_raw, int64_t R, int S, int white) {
   const int lane = threadIdx.x & 31;
@@ -325,7 +330,10 @@ k_composite_bwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
       const int i = b * 32 + lane;
       rv[b] = make_float4(0.f, 0.f, 0.f, 0.f);
       zv[b] = 0.f;
-      if (i < S) { rv[b] = ldg_stream4(rawr + i); zv[b] = ldg_stream(zr + i); }
+      if (i < S) {
+        rv[b] = ldg_stream4(rawr + i); zv[b] = ldg_stream(zr + i);
+        if (noise != nullptr) rv[b].w += ldg_stream(noise + r * S + i);
+      }
     }
     const float dn = dnorm[r];
     const float gr = g_rgb[3 * r], gg = g_rgb[3 * r + 1], gb = g_rgb[3 * r + 2];
@@ -392,7 +400,7 @@ k_composite_bwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
   }
 }
 
-int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* g_rgb,
+int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* noise, const float* g_rgb,
                          const float* g_depth, const float* g_acc, float* g_raw, int64_t R,
                          int64_t S, int white, cudaStream_t s) {
   if (R == 0) return 0;
@@ -404,25 +412,24 @@ int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, c
     const float4* raw4 = (const float4*)raw;
     float4* g4 = (float4*)g_raw;
     switch ((S + 31) / 32) {
-      case 1: k_composite_bwd_reg<1><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
-      case 2: k_composite_bwd_reg<2><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
-      case 3: case 4: k_composite_bwd_reg<4><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
-      case 5: case 6: k_composite_bwd_reg<6><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
-      default: k_composite_bwd_reg<8><<<g, t, 0, s>>>(raw4, z, dnorm, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      case 1: k_composite_bwd_reg<1><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      case 2: k_composite_bwd_reg<2><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      case 3: case 4: k_composite_bwd_reg<4><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      case 5: case 6: k_composite_bwd_reg<6><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      default: k_composite_bwd_reg<8><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
     }
     return check_launch("composite_bwd");
   }
   const size_t smem = (size_t)kBwdWarps * 2 * S * sizeof(float);
   if (smem > 200 * 1024) return set_error(FNERF_ERR_SIZE, "composite_bwd: S too large");
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_composite_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error((int)e, "composite_bwd: %s", cudaGetErrorString(e));
-  }
+  static DeviceOnce once;                            // opt in once to the 200 KB cap checked above
+  if (smem > 48 * 1024)
+    if (cudaError_t e = opt_in_smem_once(once, k_composite_bwd, 200 * 1024)) return set_error((int)e, "composite_bwd: %s", cudaGetErrorString(e));
   int64_t blocks = (R + kBwdWarps - 1) / kBwdWarps;
   const int64_t cap = (int64_t)num_sms() * 64;
   if (blocks > cap) blocks = cap;
   k_composite_bwd<<<(unsigned)blocks, kBwdWarps * 32, smem, s>>>(
-      (const float4*)raw, z, dnorm, g_rgb, g_depth, g_acc, (float4*)g_raw, R, (int)S, white);
+      (const float4*)raw, z, dnorm, noise, g_rgb, g_depth, g_acc, (float4*)g_raw, R, (int)S, white);
   return check_launch("composite_bwd");
 }
 

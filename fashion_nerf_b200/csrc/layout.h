@@ -149,6 +149,13 @@ constexpr int kTapeBwdSlots = 39;
 constexpr int kMaskUnits = 68, kMaskUnitHv = 64;
 constexpr int kMaskTileBytes = kMaskUnits * 128 * 4;
 
+// A.8: row of the [C,256] code table a ray reads.  Indices coming from the caller (cond_index) are clamped to the
+// table, so that a bad view id can never read out of bounds (the Python layer validates and raises first).
+FN_HD int64_t cond_row(const int32_t* cond_index, int64_t C, int64_t ray) {
+  int64_t row = cond_index ? (int64_t)cond_index[ray] : (C == 1 ? 0 : ray);
+  return row < 0 ? 0 : (row >= C ? C - 1 : row);
+}
+
 // swizzled byte offset of element (row r, column k in [0,64)) inside a chunk / activation K-block
 FN_HD uint32_t sw128_offset(uint32_t r, uint32_t k) {
   return r * 128u + ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));

@@ -176,7 +176,7 @@ __global__ void k_encode_chunk(const float* __restrict__ rays_o, const float* __
     xv[3 + 6 * k + 3 + c] = cs;
   }
   if (cond_rows != nullptr) {   // gather this sample's garment code into columns 63..318
-    const int64_t row = cond_index ? (int64_t)cond_index[ray] : (C == 1 ? 0 : ray);
+    const int64_t row = cond_row(cond_index, C, ray);
     const float* src = cond_rows + row * kCond;
     for (int k = c; k < kCond; k += 3) x5[kPE + k] = src[k];
   }

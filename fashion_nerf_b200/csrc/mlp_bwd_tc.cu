@@ -190,14 +190,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad_tc(const WgradBatch B) 
 // Assigns grid slices (cost = K-block images streamed per tile) and launches.
 int launch_wgrad_tc(WgradBatch& B, cudaStream_t s) {
   if (B.ntiles == 0 || B.njobs == 0) return 0;
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
-    if (e != cudaSuccess) return set_error((int)e, "wgrad_tc attr: %s", cudaGetErrorString(e));
-    attr_done[dev] = true;
-  }
+  static DeviceOnce once;
+  if (cudaError_t e = opt_in_smem_once(once, k_wgrad_tc, kWgSmem)) return set_error((int)e, "wgrad_tc attr: %s", cudaGetErrorString(e));
   const int sms = num_sms();
   if (B.njobs > kWgMaxJobs || B.njobs > sms) return set_error(FNERF_ERR_ARG, "wgrad_tc: too many jobs");
   int total_cost = 0, used = 0;
@@ -246,17 +240,25 @@ __global__ void __launch_bounds__(256) k_tape_codes(const float* __restrict__ co
     int64_t g = tile * 128 + r;
     if (g >= M) g = M - 1;
     const int64_t ray = g / S;
-    const int64_t crow = cond_index ? (int64_t)cond_index[ray] : (C == 1 ? 0 : ray);
+    const int64_t crow = cond_row(cond_index, C, ray);
     const float4* src = reinterpret_cast<const float4*>(cond_rows + crow * kCond + ch * 8);
     const float4 a = __ldg(src), b = __ldg(src + 1);
     *reinterpret_cast<uint4*>(timg + (size_t)(ch >> 3) * 16384 + r * 128u + (((ch & 7u) ^ (r & 7u)) << 4)) =
         make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
   }
 }
-// recomputing backward: forward tape | backward tape | raw scratch
-int64_t mlp_bwd_tc_workspace_bytes(int64_t M) {
-  return mlp_tape_bytes(M) + mlp_bwd_from_tape_workspace_bytes(M) + (M + 127) / 128 * 128 * 16 + 4096;
+// recomputing backward: forward tape | backward tape | raw scratch, for one chunk of whole rays (the tapes cost ~11 KB
+// per sample, so the recompute runs over chunks of at most kBwdTcChunk samples and the workspace stays bounded)
+constexpr int64_t kBwdTcChunk = 1 << 18;
+static int64_t bwd_tc_chunk_rays(int64_t R, int64_t S) {
+  int64_t rays = kBwdTcChunk / S;
+  if (rays < 1) rays = 1;
+  return rays < R ? rays : R;
 }
+static int64_t bwd_tc_chunk_bytes(int64_t M) {
+  return (mlp_tape_bytes(M) + 1023) / 1024 * 1024 + mlp_bwd_from_tape_workspace_bytes(M) + (M + 127) / 128 * 128 * 16 + 4096;
+}
+int64_t mlp_bwd_tc_workspace_bytes(int64_t R, int64_t S) { return bwd_tc_chunk_bytes(bwd_tc_chunk_rays(R, S) * S); }
 
 int launch_mlp_fwd_tape(const MlpArgs& a, void* tape, cudaStream_t s) {
   const int64_t ntiles = (a.R * a.S + 127) / 128;
@@ -322,25 +324,32 @@ int launch_mlp_bwd_from_tape(const void* packed, int cond, const float* g_raw, c
   return launch_wgrad_tc(B, s);
 }
 
-// Recomputing variant: forward with tape into the workspace, then the backward above.
+// Recomputing variant (unconditioned networks): per chunk of rays, forward with tape into the workspace, then the
+// backward above; flat_grad accumulates over the chunks.
 int launch_mlp_bwd_tc(const MlpArgs& a, const float* g_raw, float* flat_grad, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  const int64_t M = a.R * a.S;
-  if (M == 0) return 0;
-  if (ws_bytes < mlp_bwd_tc_workspace_bytes(M)) return set_error(FNERF_ERR_WORKSPACE, "mlp_bwd_tc: workspace too small");
-  uint8_t* tape = reinterpret_cast<uint8_t*>(ws);
-  uint8_t* bwd_ws = tape + (mlp_tape_bytes(M) + 1023) / 1024 * 1024;
-  MlpArgs fa = a;
-  fa.raw = reinterpret_cast<float*>(bwd_ws + mlp_bwd_from_tape_workspace_bytes(M));
-  int rc;
-  if ((rc = launch_mlp_fwd_tape(fa, tape, s))) return rc;
-  return launch_mlp_bwd_from_tape(a.packed, 0, g_raw, tape, nullptr, nullptr, 0, a.S, flat_grad, bwd_ws, M, s);
+  if (a.R * a.S == 0) return 0;
+  if (ws_bytes < mlp_bwd_tc_workspace_bytes(a.R, a.S)) return set_error(FNERF_ERR_WORKSPACE, "mlp_bwd_tc: workspace too small");
+  const int64_t chunk = bwd_tc_chunk_rays(a.R, a.S);
+  for (int64_t r0 = 0; r0 < a.R; r0 += chunk) {
+    const int64_t rays = a.R - r0 < chunk ? a.R - r0 : chunk, M = rays * a.S;
+    uint8_t* tape = reinterpret_cast<uint8_t*>(ws);
+    uint8_t* bwd_ws = tape + (mlp_tape_bytes(M) + 1023) / 1024 * 1024;
+    MlpArgs fa = a;
+    fa.rays_o = a.rays_o + 3 * r0; fa.rays_d = a.rays_d + 3 * r0; fa.viewdirs = a.viewdirs + 3 * r0; fa.z = a.z + r0 * a.S;
+    fa.R = rays;
+    fa.raw = reinterpret_cast<float*>(bwd_ws + mlp_bwd_from_tape_workspace_bytes(M));
+    int rc;
+    if ((rc = launch_mlp_fwd_tape(fa, tape, s))) return rc;
+    if ((rc = launch_mlp_bwd_from_tape(a.packed, 0, g_raw + r0 * a.S * 4, tape, nullptr, nullptr, 0, a.S, flat_grad, bwd_ws, M, s))) return rc;
+  }
+  return 0;
 }
 
 }  // namespace fnerf
 
 // ---- debug entry (tests only): dw[n_kb*64, ld] += dZ^T X from two image buffers ---------------------
 extern "C" int fnerf_debug_wgrad_tc(const void* dz_img, int n_kb, const void* x_img, int x_kb, float* dw, int64_t ld,
-                                    int n_valid, int64_t ntiles, void* stream) {
+                                    int n_valid, int64_t ntiles, fnerf_stream_t stream) {
   fnerf::WgradBatch B;
   B.njobs = 1; B.ntiles = ntiles;
   fnerf::WgradJob& P = B.jobs[0];

@@ -258,14 +258,8 @@ __global__ void __launch_bounds__(kDgThreads, 1) k_mlp_dgrad_tc(const DgradParam
 int launch_mlp_dgrad_tc(const void* packed, int cond, const float* g_raw, const uint32_t* mask_tape, uint8_t* bwd_tape,
                         float* flat_grad, int64_t M, cudaStream_t s) {
   if (M == 0) return 0;
-  static bool attr_done[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_mlp_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDgSmem);
-    if (e != cudaSuccess) return set_error((int)e, "mlp_dgrad_tc attr: %s", cudaGetErrorString(e));
-    attr_done[dev] = true;
-  }
+  static DeviceOnce once;
+  if (cudaError_t e = opt_in_smem_once(once, k_mlp_dgrad_tc, kDgSmem)) return set_error((int)e, "mlp_dgrad_tc attr: %s", cudaGetErrorString(e));
   DgradParams P;
   P.packed = reinterpret_cast<const uint8_t*>(packed); P.cond = cond;
   P.g_raw = reinterpret_cast<const float4*>(g_raw);

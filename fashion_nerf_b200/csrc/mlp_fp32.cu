@@ -122,7 +122,7 @@ k_mlp_fp32(const uint8_t* __restrict__ packed, int cond, const float* __restrict
     if (cond && threadIdx.x < kTM) {
       int64_t g = g0 + threadIdx.x; if (g >= M) g = M - 1;
       const int64_t ray = g / S;
-      const int64_t row = cond_index ? (int64_t)cond_index[ray] : (C == 1 ? 0 : ray);
+      const int64_t row = cond_row(cond_index, C, ray);
       s_rowbias[threadIdx.x] = cond_proj + row * kW;
     }
     __syncthreads();
@@ -177,13 +177,8 @@ k_mlp_fp32(const uint8_t* __restrict__ packed, int cond, const float* __restrict
 int launch_mlp_fp32(const MlpArgs& a, cudaStream_t s) {
   const int64_t M = a.R * a.S;
   if (M == 0) return 0;
-  static bool attr_done[64] = {false};
-  int dev = 0; cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_mlp_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFp32Smem);
-    if (e != cudaSuccess) return set_error((int)e, "mlp_fp32 attr: %s", cudaGetErrorString(e));
-    attr_done[dev] = true;
-  }
+  static DeviceOnce once;
+  if (cudaError_t e = opt_in_smem_once(once, k_mlp_fp32, kFp32Smem)) return set_error((int)e, "mlp_fp32 attr: %s", cudaGetErrorString(e));
   const int64_t ntiles = (M + kTM - 1) / kTM;
   int64_t blocks = num_sms();
   if (blocks > ntiles) blocks = ntiles;

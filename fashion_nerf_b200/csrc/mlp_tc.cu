@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
 
       const float* rowbias = nullptr;
       if (P.cond) {
-        const int64_t crow = P.cond_index ? (int64_t)P.cond_index[ray] : (P.C == 1 ? 0 : ray);
+        const int64_t crow = cond_row(P.cond_index, P.C, ray);
         rowbias = P.cond_proj + crow * kW;
       }
       float sigma = 0.0f;                                   // this thread's share of the sigma head
@@ -593,23 +593,23 @@ extern "C" int fnerf_debug_set_trace(long long* buf) {
 // (mlp_dgrad_tc.cu / mlp_bwd_tc.cu consume them).
 template <int kCl>
 static int launch_mlp_tc_cluster(const TcParams& P, cudaStream_t s) {
-  static int max_clusters[64] = {0};                 // 0 = not queried, < 0 = clusters unavailable
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
+  static DeviceOnce once;
+  static int max_clusters[kMaxDevices];              // < 0 = clusters unavailable
+  const int dev = current_device();
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kTcSmemBytes; cfg.stream = s; cfg.attrs = attr; cfg.numAttrs = 1;
-  if (max_clusters[dev] == 0) {
+  device_once(once, [&] {
     cudaError_t e = cudaFuncSetAttribute(k_mlp_tc<false, kCl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     int n = 0;
     cfg.gridDim = dim3((unsigned)(num_sms() / kCl * kCl));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, k_mlp_tc<false, kCl>, &cfg);
     max_clusters[dev] = (e == cudaSuccess && n > 0) ? n : -1;
     (void)cudaGetLastError();
-  }
+    return cudaSuccess;
+  });
   if (max_clusters[dev] < 0) return -1;              // caller falls back to the single-CTA kernel
   int64_t clusters = max_clusters[dev];
   const int64_t want = (P.ntiles + kCl - 1) / kCl;
@@ -622,28 +622,23 @@ static int launch_mlp_tc_cluster(const TcParams& P, cudaStream_t s) {
 
 // render kernel as single CTAs (1) or CTA pairs (2): FNERF_MLP_CLUSTER overrides the default
 static int mlp_cluster_size() {
-  static int v = -1;
-  if (v < 0) {
+  static std::once_flag flag;
+  static int v = kDefaultMlpCluster;
+  std::call_once(flag, [] {
     const char* e = getenv("FNERF_MLP_CLUSTER");
     v = e ? atoi(e) : kDefaultMlpCluster;
     if (v != 1 && v != 2) v = 1;
-  }
+  });
   return v;
 }
 
 int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cudaStream_t s) {
   const int64_t M = a.R * a.S;
   if (M == 0) return 0;
-  static bool attr_done[64][2] = {{false}};
-  int dev = 0;
-  cudaGetDevice(&dev);
+  static DeviceOnce once[2];
   const int sv = tape != nullptr ? 1 : 0;
-  if (dev >= 0 && dev < 64 && !attr_done[dev][sv]) {
-    cudaError_t e = sv ? cudaFuncSetAttribute(k_mlp_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)
-                       : cudaFuncSetAttribute(k_mlp_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
-    if (e != cudaSuccess) return set_error((int)e, "mlp_tc attr: %s", cudaGetErrorString(e));
-    attr_done[dev][sv] = true;
-  }
+  if (cudaError_t e = sv ? opt_in_smem_once(once[1], k_mlp_tc<true, 1>, kTcSmemBytes) : opt_in_smem_once(once[0], k_mlp_tc<false, 1>, kTcSmemBytes))
+    return set_error((int)e, "mlp_tc attr: %s", cudaGetErrorString(e));
   TcParams P;
   P.packed = reinterpret_cast<const uint8_t*>(a.packed);
   P.rays_o = a.rays_o; P.rays_d = a.rays_d; P.viewdirs = a.viewdirs; P.z = a.z;

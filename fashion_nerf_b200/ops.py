@@ -141,9 +141,9 @@ def mlp_bwd(packed: torch.Tensor, rays_o, rays_d, viewdirs, z, g_raw: torch.Tens
                                           _f32(viewdirs, "viewdirs"), _f32(z, "z"), _f32(g_raw, "g_raw"))
     R, S = z.shape
     lib = _lib.load()
-    ws_bytes = int(lib.fnerf_mlp_bwd_workspace_bytes(R, S))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
     has_cond = cond_rows is not None
+    ws_bytes = int(lib.fnerf_mlp_bwd_workspace_bytes(PRECISIONS[precision], int(has_cond), R, S))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=z.device)
     if has_cond:
         cond_rows = _f32(cond_rows, "cond_rows").reshape(-1, 256)
     C = cond_rows.shape[0] if has_cond else 0
@@ -254,17 +254,20 @@ def composite_fwd(raw: torch.Tensor, z: torch.Tensor, dnorm: torch.Tensor, *, wh
 
 def composite_bwd(raw: torch.Tensor, z: torch.Tensor, dnorm: torch.Tensor, g_rgb: torch.Tensor,
                   g_depth: Optional[torch.Tensor] = None, g_acc: Optional[torch.Tensor] = None, *,
-                  white_bkgd: bool = False) -> torch.Tensor:
-    """A.6 -> g_raw[R,S,4]."""
+                  white_bkgd: bool = False, raw_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A.6 -> g_raw[R,S,4].  raw_noise: the tensor composite_fwd was given (sigma = raw[...,3] + raw_noise)."""
     raw, z, dnorm, g_rgb = _f32(raw, "raw"), _f32(z, "z"), _f32(dnorm, "dnorm"), _f32(g_rgb, "g_rgb")
     R, S = z.shape
     if g_depth is not None:
         g_depth = _f32(g_depth, "g_depth")
     if g_acc is not None:
         g_acc = _f32(g_acc, "g_acc")
+    if raw_noise is not None:
+        raw_noise = _f32(raw_noise, "raw_noise")
+        assert raw_noise.shape == (R, S)
     g_raw = torch.empty(R, S, 4, dtype=torch.float32, device=z.device)
     with torch.cuda.device(z.device):
-        check(_lib.load().fnerf_composite_bwd(raw.data_ptr(), z.data_ptr(), dnorm.data_ptr(), g_rgb.data_ptr(),
+        check(_lib.load().fnerf_composite_bwd(raw.data_ptr(), z.data_ptr(), dnorm.data_ptr(), _ptr(raw_noise), g_rgb.data_ptr(),
                                               _ptr(g_depth), _ptr(g_acc), g_raw.data_ptr(), R, S, int(white_bkgd),
                                               _stream()), "composite_bwd")
     return g_raw

@@ -4,8 +4,9 @@ gradient buffer of both networks (1,191,688 floats = 4.77 MB), Adam on the fp32 
 re-pack of the kernel blobs.  One process per GPU; ``torch.distributed`` (NCCL over NVLink on the
 B200 box, gloo in the CPU tests) is used for nothing but that all-reduce.
 
-The host-side pieces (`allreduce_mean_`, `FlatAdam`) are plain torch so the world_size>1 logic is
-testable on CPU; the gradient computation itself has no CPU path."""
+The host-side control flow (`allreduce_mean_`, `FlatAdam`'s step bookkeeping) is plain torch so the world_size>1 logic
+is testable on CPU with gloo; every arithmetic step -- gradients AND the optimiser update -- is a CUDA kernel of
+libfnerf.so.  (The CPU tests inject their own update function into `FlatAdam`; the product has no CPU mirror.)"""
 from __future__ import annotations
 
 import math
@@ -28,10 +29,18 @@ def allreduce_mean_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
     return flat_grad
 
 
-class FlatAdam:
-    """Adam (torch defaults: betas 0.9/0.999, eps 1e-8; A.10) over one flat fp32 parameter buffer."""
+def _fused_adam_kernel(params, grad, m, v, t, lr, b1, b2, eps, grad_scale):
+    from . import ops
+    ops.adam_step(params, grad.contiguous(), m, v, t, lr=lr, betas=(b1, b2), eps=eps, grad_scale=grad_scale)
 
-    def __init__(self, n: int, device, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+
+class FlatAdam:
+    """Adam (torch defaults: betas 0.9/0.999, eps 1e-8; A.10) over one flat fp32 parameter buffer.  The update itself
+    is `update_fn(params, grad, m, v, t, lr, b1, b2, eps, grad_scale)`: the fused CUDA kernel ``fnerf_adam_step`` unless
+    a test injects another one."""
+
+    def __init__(self, n: int, device, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, update_fn=None):
+        self.update_fn = update_fn or _fused_adam_kernel
         self.lr, self.b1, self.b2, self.eps = lr, betas[0], betas[1], eps
         self.m = torch.zeros(n, dtype=torch.float32, device=device)
         self.v = torch.zeros(n, dtype=torch.float32, device=device)
@@ -48,18 +57,7 @@ class FlatAdam:
         """Update `params` (a view of the flat buffer starting at `offset`) at the current step count."""
         n = params.numel()
         m, v = self.m[offset:offset + n], self.v[offset:offset + n]
-        if params.is_cuda:                       # one fused kernel; the torch expression below is the CPU-test mirror
-            from . import ops
-            ops.adam_step(params, grad.contiguous(), m, v, self.t, lr=self.lr, betas=(self.b1, self.b2), eps=self.eps,
-                          grad_scale=grad_scale)
-            return
-        if grad_scale != 1.0:
-            grad = grad * grad_scale
-        m.mul_(self.b1).add_(grad, alpha=1 - self.b1)
-        v.mul_(self.b2).addcmul_(grad, grad, value=1 - self.b2)
-        bc1, bc2 = 1 - self.b1 ** self.t, 1 - self.b2 ** self.t
-        denom = (v / bc2).sqrt_().add_(self.eps)
-        params.addcdiv_(m, denom, value=-self.lr / bc1)
+        self.update_fn(params, grad, m, v, self.t, self.lr, self.b1, self.b2, self.eps, grad_scale)
 
 
 class Trainer:
@@ -83,19 +81,29 @@ class Trainer:
         self.nvls = False
         self.flat_grad = None
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = world
         if world > 1 and (fused_allreduce or (fused_allreduce is None and world <= 4)) and model.device.type == "cuda":
+            err = None
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 buf = symm_mem.empty(n, dtype=torch.float32, device=model.device)
                 self.symm = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
-                self.flat_grad = buf.zero_()
                 self.nvls = fused_allreduce == "nvls"
                 if self.nvls and (not self.symm.multicast_ptr or n % 4):
                     raise RuntimeError("no NVSwitch multicast mapping for the gradient buffer")
-            except Exception as e:                     # no P2P / fabric handles: fall back to NCCL
+            except Exception as e:                     # no P2P / fabric handles on this rank
+                err = e
+            # the ranks must AGREE on the mode: a rank that fell back to NCCL while its peers wait in a symmetric-memory
+            # barrier would deadlock the job
+            ok = torch.tensor([0 if err is not None else 1], device=model.device, dtype=torch.int32)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                self.flat_grad = buf.zero_()
+            else:
+                self.symm, self.nvls = None, False
                 if fused_allreduce:
-                    raise
-                self.symm = None
+                    raise RuntimeError(f"fused all-reduce ({fused_allreduce!r}) unavailable on at least one rank"
+                                       + (f": {err}" if err is not None else ""))
         if self.flat_grad is None:
             self.flat_grad = torch.zeros(n, dtype=torch.float32, device=model.device)   # the all-reduce buffer
 
@@ -106,11 +114,14 @@ class Trainer:
         fc = m.coarse.flat.detach().requires_grad_(True)
         ff = fc if self.shared else m.fine.flat.detach().requires_grad_(True)
         m.coarse.flat, m.fine.flat = fc, ff
-        out = render_rays(m, rays_o, rays_d, near, far, N_samples, N_importance, cond, view_id=view_id,
-                          u_strat=u_strat, u_fine=u_fine, white_bkgd=white_bkgd, precision=precision)
-        loss_f = ((out["rgb"] - target) ** 2).mean()
-        loss = loss_f + ((out["rgb0"] - target) ** 2).mean() if N_importance > 0 else loss_f
-        loss.backward()
+        try:
+            out = render_rays(m, rays_o, rays_d, near, far, N_samples, N_importance, cond, view_id=view_id,
+                              u_strat=u_strat, u_fine=u_fine, white_bkgd=white_bkgd, precision=precision)
+            loss_f = ((out["rgb"] - target) ** 2).mean()
+            loss = loss_f + ((out["rgb0"] - target) ** 2).mean() if N_importance > 0 else loss_f
+            loss.backward()
+        finally:                                  # never leave autograd leaves behind in the model
+            m.coarse.flat, m.fine.flat = fc.detach(), ff.detach()
         with torch.no_grad():
             g = self.flat_grad
             g[:self.n_c].copy_(fc.grad)
@@ -119,7 +130,6 @@ class Trainer:
                     g[self.n_c:].copy_(ff.grad)
                 else:
                     g[self.n_c:].zero_()
-            m.coarse.flat, m.fine.flat = fc.detach(), ff.detach()
             self.opt.t += 1
             if self.symm is not None:
                 # every rank's gradients are in its symmetric buffer: barrier, then each rank sums all peers' buffers over

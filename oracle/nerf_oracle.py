@@ -192,7 +192,8 @@ def raw2outputs(raw: torch.Tensor, z: torch.Tensor, dnorm: torch.Tensor,
 # --------------------------------------------------------------------------- A.6
 def composite_bwd(raw: torch.Tensor, z: torch.Tensor, dnorm: torch.Tensor,
                   g_rgb: torch.Tensor, g_depth: Optional[torch.Tensor] = None,
-                  g_acc: Optional[torch.Tensor] = None, white_bkgd: bool = False) -> torch.Tensor:
+                  g_acc: Optional[torch.Tensor] = None, white_bkgd: bool = False,
+                  raw_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
     """closed-form dL/draw [R,S,4] given dL/d(rgb_map, depth_map, acc_map).
 
     (disp_map carries no gradient in the training loss, A.10.)
@@ -203,6 +204,8 @@ def composite_bwd(raw: torch.Tensor, z: torch.Tensor, dnorm: torch.Tensor,
     dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full_like(z[:, :1], 1e10)], -1) * dnorm[:, None]
     rgb = torch.sigmoid(raw[..., :3])
     sigma = raw[..., 3]
+    if raw_noise is not None:
+        sigma = sigma + raw_noise
     alpha = 1.0 - torch.exp(-torch.relu(sigma) * dists)
     one_m = 1.0 - alpha + 1e-10
     T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), one_m], -1), -1)[:, :-1]
@@ -248,13 +251,15 @@ def sample_pdf(z_c: torch.Tensor, weights_c: torch.Tensor, u: torch.Tensor):
 
 # --------------------------------------------------------------------------- A.9
 def render_rays(params_c, params_f, rays_o, rays_d, near, far, N_samples, N_importance,
-                cond_rows=None, *, u_strat=None, u_fine=None, white_bkgd=False, lindisp=False,
+                cond_rows=None, *, u_strat=None, u_fine=None, raw_noise=None, white_bkgd=False, lindisp=False,
                 bf16=False, z_f_override=None, return_extras=False):
     """coarse -> composite -> importance -> fine -> composite.
 
     near/far: floats or [R] tensors.  cond_rows: [R,256] or None (already gathered per ray).
-    ``z_f_override`` teacher-forces the fine depths (H6).  All fp32, CPU.
+    ``z_f_override`` teacher-forces the fine depths (H6).  ``raw_noise``: None or a pair
+    (coarse [R,N_samples], fine [R,N_samples+N_importance]) added to sigma_raw before the ReLU (A.5).  All fp32, CPU.
     """
+    noise_c, noise_f = (None, None) if raw_noise is None else raw_noise
     R = rays_o.shape[0]
     near = torch.full((R,), float(near)) if not torch.is_tensor(near) else near.reshape(R).float()
     far = torch.full((R,), float(far)) if not torch.is_tensor(far) else far.reshape(R).float()
@@ -263,7 +268,7 @@ def render_rays(params_c, params_f, rays_o, rays_d, near, far, N_samples, N_impo
     z_c = stratified(near, far, t_vals, u_strat, lindisp)
     pts = rays_o[:, None, :] + rays_d[:, None, :] * z_c[:, :, None]
     raw_c = run_network(params_c, pts, viewdirs, cond_rows, bf16=bf16)
-    out_c = raw2outputs(raw_c, z_c, dnorm, white_bkgd)
+    out_c = raw2outputs(raw_c, z_c, dnorm, white_bkgd, noise_c)
     res = {"rgb0": out_c["rgb"], "disp0": out_c["disp"], "acc0": out_c["acc"], "depth0": out_c["depth"]}
     extras = {"z_c": z_c, "raw_c": raw_c, "weights_c": out_c["weights"], "dnorm": dnorm, "viewdirs": viewdirs}
     if N_importance > 0:
@@ -273,7 +278,7 @@ def render_rays(params_c, params_f, rays_o, rays_d, near, far, N_samples, N_impo
         z_f = sp["z_f"] if z_f_override is None else z_f_override
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z_f[:, :, None]
         raw_f = run_network(params_f, pts, viewdirs, cond_rows, bf16=bf16)
-        out_f = raw2outputs(raw_f, z_f, dnorm, white_bkgd)
+        out_f = raw2outputs(raw_f, z_f, dnorm, white_bkgd, noise_f)
         res.update({"rgb": out_f["rgb"], "disp": out_f["disp"], "acc": out_f["acc"],
                     "depth": out_f["depth"], "z_std": sp["z_std"]})
         extras.update({"z_f": z_f, "raw_f": raw_f, "weights_f": out_f["weights"], "inds": sp["inds"],

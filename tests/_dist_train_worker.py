@@ -38,6 +38,9 @@ for r in range(world):
 ref_c = O.adam_step({k: v.clone() for k, v in pc.items()}, {k: v / world for k, v in gc_sum.items()}, {})
 ref_f = O.adam_step({k: v.clone() for k, v in pf.items()}, {k: v / world for k, v in gf_sum.items()}, {})
 ref_c, ref_f = F.flatten_state_dict(ref_c), F.flatten_state_dict(ref_f)
+p0_c, p0_f = F.flatten_state_dict(pc), F.flatten_state_dict(pf)
+gmean_c = F.flatten_state_dict({k: v / world for k, v in gc_sum.items()})
+gmean_f = F.flatten_state_dict({k: v / world for k, v in gf_sum.items()})
 
 o, d, tgt, u_s, u_f = (t.to(dev) for t in rank_data(rank))
 ok = True
@@ -59,12 +62,22 @@ for mode in (False, True, "nvls"):
     allc = [torch.empty_like(chk) for _ in range(world)]
     dist.all_gather(allc, chk)
     same = all(torch.equal(allc[0], c) for c in allc)
-    # Adam's first step moves every parameter by ~lr * sign(g): compare against the oracle with a tolerance of lr/2 on the
-    # few parameters whose gradient is at rounding level, and tightly on average
+    # Adam's first step moves every parameter by -lr * g / (|g| + eps) ~ -lr * sign(g).  A bound of ~2 lr on the parameters
+    # would let a parameter step the WRONG way and pass, so: every parameter whose mean oracle gradient is above the fp32
+    # path's rounding level (1e-3 of its tensor's largest gradient, at least 1e-6) must move against that gradient, and
+    # the parameters must agree with the oracle's tightly on average.
+    wrong = 0
+    for net, ref_g, p0 in ((model.coarse, gmean_c, p0_c), (model.fine, gmean_f, p0_f)):
+        delta = net.flat.cpu() - p0
+        thr = torch.cat([torch.full((v.numel(),), max(1e-6, 1e-3 * v.abs().max().item())) for v in F.unflatten(ref_g).values()])
+        sure = ref_g.abs() > thr
+        wrong += int((torch.sign(delta[sure]) != -torch.sign(ref_g[sure])).sum())
     mean_c = (model.coarse.flat.cpu() - ref_c).abs().mean().item()
-    good = same and ec <= 1.1e-3 and ef <= 1.1e-3 and mean_c <= 2e-5
+    mean_f = (model.fine.flat.cpu() - ref_f).abs().mean().item()
+    good = same and wrong == 0 and mean_c <= 2e-5 and mean_f <= 2e-5
     ok = ok and good
-    print(f"rank {rank} mode {mode}: max|dparam| coarse {ec:.2e} fine {ef:.2e} mean {mean_c:.2e} replicas_identical {same}", flush=True)
+    print(f"rank {rank} mode {mode}: wrong-way steps {wrong}, max|dparam| coarse {ec:.2e} fine {ef:.2e} mean {mean_c:.2e} / {mean_f:.2e} "
+          f"replicas_identical {same}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 print("DIST_OK" if ok else "DIST_FAIL", flush=True)

@@ -64,3 +64,41 @@ def test_bad_checkpoints_are_rejected():
         C.validate_state_dict(bad)
     with pytest.raises(ValueError):
         C.make_checkpoint(sd, init_state_dict(1, cond=True)) and C.read_checkpoint(C.make_checkpoint(sd, init_state_dict(1, cond=True)))
+
+
+class _FakeTrainer:
+    def __init__(self, n):
+        from fashion_nerf_b200.train import FlatAdam
+        self.opt = FlatAdam(n, "cpu")
+
+
+def test_canonical_torch_adam_state_is_converted_to_the_flat_layout():
+    """A checkpoint written by the canonical training loop carries torch.optim.Adam's {'state','param_groups'} over
+    list(model.parameters()) + list(model_fine.parameters()); restore_optimizer maps it onto the flat buffers
+    (module order -> flat order differs: views_linears comes before feature/alpha in the module)."""
+    torch.manual_seed(1)
+    mc, mf = CanonicalNeRF(), CanonicalNeRF()
+    opt = torch.optim.Adam(list(mc.parameters()) + list(mf.parameters()), lr=3e-4, betas=(0.8, 0.95), eps=1e-7)
+    for _ in range(3):
+        for p in list(mc.parameters()) + list(mf.parameters()):
+            p.grad = torch.randn_like(p)
+        opt.step()
+    ck = {"global_step": 3, "network_fn_state_dict": mc.state_dict(), "network_fine_state_dict": mf.state_dict(),
+          "optimizer_state_dict": opt.state_dict()}
+    got = C.read_checkpoint(ck)
+    n = sum(p.numel() for p in mc.parameters())
+    tr = _FakeTrainer(2 * n)
+    C.restore_optimizer(tr, got)
+    assert tr.opt.t == 3 and tr.opt.lr == 3e-4 and (tr.opt.b1, tr.opt.b2) == (0.8, 0.95) and tr.opt.eps == 1e-7
+    # the flat layout is pts 0..7, alpha, feature, views, rgb: compare tensor by tensor through unflatten
+    for net, (module, lo) in enumerate(((mc, 0), (mf, n))):
+        moments = unflatten(tr.opt.m[lo:lo + n])
+        sq = unflatten(tr.opt.v[lo:lo + n])
+        for name, p in module.named_parameters():
+            st = opt.state[p]
+            assert torch.equal(moments[name], st["exp_avg"]) and torch.equal(sq[name], st["exp_avg_sq"]), (net, name)
+    # a malformed optimizer dictionary is a clear ValueError, not a KeyError
+    with pytest.raises(ValueError):
+        C.restore_optimizer(tr, {"optimizer": {"foo": 1}, "cond": False, "fine": None})
+    with pytest.raises(ValueError):
+        C.restore_optimizer(_FakeTrainer(n), got)          # one network's worth of state buffers

@@ -4,9 +4,14 @@ partition the frame without overlap."""
 import os
 import socket
 
+import sys
+
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _cpu_adam import cpu_adam_update  # noqa: E402
 
 
 def _free_port():
@@ -24,7 +29,7 @@ def _worker(rank, world, port, out):
     n = 1_191_688                                                     # coarse + fine flat parameters
     g = torch.Generator().manual_seed(7)
     params = torch.randn(n, generator=g)
-    opt = FlatAdam(n, "cpu")
+    opt = FlatAdam(n, "cpu", update_fn=cpu_adam_update)
     for step in range(3):
         # per-rank "local" gradient of a quadratic loss on this rank's shard of a synthetic batch
         data = torch.randn(n, generator=torch.Generator().manual_seed(100 * step + rank))
@@ -55,7 +60,7 @@ def test_allreduce_adam_two_ranks_match_single_process():
     from fashion_nerf_b200.train import FlatAdam
     n = 1_191_688
     params = torch.randn(n, generator=torch.Generator().manual_seed(7))
-    opt = FlatAdam(n, "cpu")
+    opt = FlatAdam(n, "cpu", update_fn=cpu_adam_update)
     for step in range(3):
         grads = [params - torch.randn(n, generator=torch.Generator().manual_seed(100 * step + r)) for r in range(world)]
         opt.step(params, (grads[0] + grads[1]) / world)
@@ -68,13 +73,23 @@ def test_flat_adam_matches_torch_optim():
     p0 = torch.randn(1000, generator=g)
     a = p0.clone()
     b = p0.clone().requires_grad_(True)
-    mine, ref = FlatAdam(1000, "cpu", lr=5e-4), torch.optim.Adam([b], lr=5e-4)
+    mine, ref = FlatAdam(1000, "cpu", lr=5e-4, update_fn=cpu_adam_update), torch.optim.Adam([b], lr=5e-4)
     for _ in range(5):
         grad = torch.randn(1000, generator=g)
         mine.step(a, grad)
         b.grad = grad.clone()
         ref.step()
     assert torch.allclose(a, b.detach(), atol=1e-7)
+
+
+def test_flat_adam_has_no_cpu_arithmetic_of_its_own():
+    """Without an injected update function the optimiser goes to the CUDA kernel and refuses CPU buffers."""
+    import pytest
+    from fashion_nerf_b200 import FnerfError
+    from fashion_nerf_b200.train import FlatAdam
+    opt = FlatAdam(8, "cpu")
+    with pytest.raises(FnerfError):
+        opt.step(torch.zeros(8), torch.ones(8))
 
 
 def test_ray_shards_partition_the_frame():

@@ -314,3 +314,28 @@ def test_importance_ties_and_duplicates(F, cuda_device):
     got = F.ops.importance(z.to(cuda_device), w.to(cuda_device), u.to(cuda_device))
     assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
     assert torch.equal(got["z_f"].cpu(), ref["z_f"])
+
+
+@pytest.mark.parametrize("R,S,white", [(300, 64, False), (40, 300, True)])
+def test_composite_bwd_with_raw_noise(F, cuda_device, R, S, white):
+    """A.6 with the forward's raw_noise: sigma = raw[...,3] + noise decides alpha AND the ReLU gate (both the
+    register-resident and the shared-memory kernel)."""
+    g = torch.Generator().manual_seed(S)
+    raw = torch.randn(R, S, 4, generator=g)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0]
+    dn = 1 + torch.rand(R, generator=g)
+    nz = torch.randn(R, S, generator=g)
+    g_rgb, g_d, g_a = torch.randn(R, 3, generator=g), torch.randn(R, generator=g), torch.randn(R, generator=g)
+    want = O.composite_bwd(raw.double(), z.double(), dn.double(), g_rgb.double(), g_d.double(), g_a.double(), white, nz.double())
+    dev = cuda_device
+    got = F.ops.composite_bwd(raw.to(dev), z.to(dev), dn.to(dev), g_rgb.to(dev), g_d.to(dev), g_a.to(dev), white_bkgd=white,
+                              raw_noise=nz.to(dev)).cpu()
+    ref32 = O.composite_bwd(raw, z, dn, g_rgb, g_d, g_a, white, nz)
+    scale = want.abs().max().item()
+    assert torch.isfinite(got).all()
+    assert (got.double() - want).abs().max().item() <= max(4 * (ref32.double() - want).abs().max().item(), 1e-5 * max(scale, 1.0))
+    plain = O.composite_bwd(raw.double(), z.double(), dn.double(), g_rgb.double(), g_d.double(), g_a.double(), white)
+    assert (plain - want).abs().max().item() > 1e-2 * scale          # the noise changes the answer: the test has teeth
+    fwd = F.ops.composite_fwd(raw.to(dev), z.to(dev), dn.to(dev), white_bkgd=white, raw_noise=nz.to(dev))
+    ref = O.raw2outputs(raw, z, dn, white, nz)
+    assert (fwd["rgb"].cpu() - ref["rgb"]).abs().max() <= 1e-5 and (fwd["weights"].cpu() - ref["weights"]).abs().max() <= 1e-5

@@ -89,11 +89,13 @@ def test_bf16_path_free_running(F, cfg1, cuda_device):
     err0 = (out["rgb0"][~flip_c] - ref["rgb0"][~flip_c]).abs().max().item()
     dpsnr = abs(O.psnr(out["rgb"][keep], tgt[keep]) - O.psnr(ref["rgb"][keep], tgt[keep]))
     dpsnr_all = abs(O.psnr(out["rgb"], tgt) - O.psnr(ref["rgb"], tgt))
-    print(f"free-running bf16: {int((~keep).sum())} far-opacity flips excluded; rgb max abs {err:.3e}, rgb0 {err0:.3e}, "
-          f"|dPSNR| {dpsnr:.2e} dB (all rays incl. flips: {dpsnr_all:.2e} dB)")
-    assert keep.float().mean() > 0.95
-    assert err <= 2e-3 and err0 <= 2e-3
-    assert dpsnr <= 0.01
+    n_flip = int((~keep).sum())
+    print(f"free-running bf16: FLIPS {n_flip} of 4096 rays change far-sample opacity (|sigma_far| <= tol) and are excluded "
+          f"from the per-pixel bound; rgb max abs {err:.3e}, rgb0 {err0:.3e}, |dPSNR| {dpsnr:.2e} dB, "
+          f"|dPSNR| over ALL rays incl. flips {dpsnr_all:.2e} dB")
+    assert n_flip <= 16                      # 8 of 4096 measured; the escape hatch stays this narrow
+    assert err <= 2e-3 and err0 <= 2e-3      # north_star: per-pixel RGB <= 2e-3 abs
+    assert dpsnr <= 0.01 and dpsnr_all <= 0.01      # north_star: PSNR delta <= 0.01 dB, asserted over EVERY ray too
     assert (out["acc"][keep] - ref["acc"][keep]).abs().max() <= 2e-3
 
 
@@ -109,12 +111,14 @@ def test_bf16_path_teacher_forced(F, cfg1, cuda_device):
     rgb = out["rgb"].cpu()
     err = (rgb[keep] - ref["rgb"][keep]).abs().max().item()
     dpsnr = abs(O.psnr(rgb[keep], c["tgt"][keep]) - O.psnr(ref["rgb"][keep], c["tgt"][keep]))
-    print(f"teacher-forced bf16: {int((~keep).sum())} far-opacity flips excluded; rgb max abs {err:.3e}, "
-          f"raw max abs {raw_err:.3e}, |dPSNR| {dpsnr:.2e} dB")
-    assert keep.float().mean() > 0.95
+    dpsnr_all = abs(O.psnr(rgb, c["tgt"]) - O.psnr(ref["rgb"], c["tgt"]))
+    n_flip = int((~keep).sum())
+    print(f"teacher-forced bf16: FLIPS {n_flip} of 4096 excluded; rgb max abs {err:.3e}, "
+          f"raw max abs {raw_err:.3e}, |dPSNR| {dpsnr:.2e} dB, over ALL rays {dpsnr_all:.2e} dB")
+    assert n_flip <= 16
     assert raw_err <= 2e-3
     assert err <= 2e-3
-    assert dpsnr <= 0.01
+    assert dpsnr <= 0.01 and dpsnr_all <= 0.01
 
 
 def test_deterministic_sampling_defaults(F, cfg1, cuda_device):
@@ -307,3 +311,104 @@ print("CHK", out)
         assert p.returncode == 0, p.stderr[-2000:]
         res[mode] = [l for l in p.stdout.splitlines() if l.startswith("CHK")][0]
     assert res["1"] == res["2"], res
+
+
+def test_render_image_matches_oracle_on_a_64x64_frame(F, cfg1, cuda_device):
+    """the full-frame tiler (ragged chunks) against the ORACLE, not against itself: fp32 path <= 2e-4,
+    bf16 path <= 2e-3 per pixel outside the far-opacity flips."""
+    c, dev, ref = cfg1, cuda_device, cfg1["ref"]
+    o, d = F.pinhole_rays(64, 64, device=dev)              # the package's camera, not the oracle's
+    for prec, tol, raw_tol in (("fp32", 2e-4, 1e-4), ("bf16", 2e-3, 4e-3)):
+        img = F.render_image(c["model"], o, d, 2.0, 6.0, NC, NF, chunk=1237, u_strat=c["u_s"].to(dev), u_fine=c["u_f"].to(dev),
+                             precision=prec)
+        with torch.no_grad():
+            taps = F.render_rays(c["model"], o, d, 2.0, 6.0, NC, NF, u_strat=c["u_s"].to(dev), u_fine=c["u_f"].to(dev),
+                                 precision=prec, return_taps=True)
+        keep = ~(_far_flips(taps["raw_c"].cpu(), ref["extras"]["raw_c"], raw_tol) | _far_flips(taps["raw_f"].cpu(), ref["extras"]["raw_f"], raw_tol))
+        assert int((~keep).sum()) <= 16
+        err = (img["rgb"].cpu()[keep] - ref["rgb"][keep]).abs().max().item()
+        print(f"render_image {prec}: rgb max abs vs oracle {err:.3e} ({int((~keep).sum())} flips excluded)")
+        assert img["rgb"].shape == (4096, 3) and err <= tol, (prec, err)
+        assert (img["acc"].cpu()[keep] - ref["acc"][keep]).abs().max() <= tol
+
+
+def test_conditioned_cfg5_shape_slice(F, cuda_device):
+    """BASELINE configs[4] shape: V = 32 views of 512x512 with one 256-d code per view, 64+128 samples.  A slice of
+    2048 rays spread over four of the views (code table [32,256] + view_id per ray) against the oracle."""
+    dev = cuda_device
+    V, per_view = 32, 512
+    pc, pf = O.init_params(0, cond=True), O.init_params(1, cond=True)
+    pc["alpha_linear.bias"] += 0.1
+    pf["alpha_linear.bias"] += 0.1
+    cond = 0.25 * torch.randn(V, 256, generator=torch.Generator().manual_seed(2))
+    os_, ds_, ids = [], [], []
+    for v in (0, 7, 19, 31):
+        o, d = O.pinhole_rays(512, 512, view=v, n_views=V)
+        idx = torch.linspace(0, 512 * 512 - 1, per_view).long()
+        os_.append(o[idx]); ds_.append(d[idx]); ids.append(torch.full((per_view,), v))
+    o, d, view_id = torch.cat(os_), torch.cat(ds_), torch.cat(ids)
+    R = o.shape[0]
+    g = torch.Generator().manual_seed(0)
+    u_s, u_f = torch.rand(R, NC, generator=g), torch.rand(R, NF, generator=g)
+    with torch.no_grad():
+        ref = O.render_rays(pc, pf, o, d, 2.0, 6.0, NC, NF, cond[view_id], u_strat=u_s, u_fine=u_f, return_extras=True)
+    model = F.NerfModel(F.NerfNetwork.from_state_dict(pc, dev, cond=True), F.NerfNetwork.from_state_dict(pf, dev, cond=True))
+    for prec, tol, raw_tol in (("fp32", 2e-4, 1e-4), ("bf16", 2e-3, 4e-3)):
+        with torch.no_grad():
+            out = F.render_rays(model, o.to(dev), d.to(dev), 2.0, 6.0, NC, NF, cond.to(dev), view_id=view_id.to(dev),
+                                u_strat=u_s.to(dev), u_fine=u_f.to(dev), precision=prec, return_taps=True)
+        assert torch.equal(out["z_c"].cpu(), ref["extras"]["z_c"])
+        keep = ~(_far_flips(out["raw_c"].cpu(), ref["extras"]["raw_c"], raw_tol) | _far_flips(out["raw_f"].cpu(), ref["extras"]["raw_f"], raw_tol))
+        err = (out["rgb"].cpu()[keep] - ref["rgb"][keep]).abs().max().item()
+        print(f"cfg5 slice {prec}: rgb max abs {err:.3e}, {int((~keep).sum())} flips excluded")
+        assert int((~keep).sum()) <= 16 and err <= tol, (prec, err)
+    # the four views must actually differ through their codes
+    assert (ref["rgb"][:per_view] - ref["rgb"][per_view:2 * per_view]).abs().max() > 1e-3
+
+
+def test_view_id_out_of_range_is_rejected(F, cuda_device):
+    """a view id outside [0, V) must raise on the host instead of reading the code table out of bounds."""
+    dev = cuda_device
+    model = F.NerfModel.random(dev, cond=True)
+    o, d = F.pinhole_rays(8, 8, device=dev)
+    cond = torch.randn(4, 256, device=dev)
+    for bad in (torch.full((64,), 4), torch.full((64,), -1), torch.arange(64) - 1):
+        with pytest.raises(ValueError):
+            F.render_rays(model, o, d, 2.0, 6.0, 16, 16, cond, view_id=bad.to(dev))
+    with pytest.raises(ValueError):
+        F.render_rays(model, o, d, 2.0, 6.0, 16, 16, cond, view_id=torch.zeros(63, dtype=torch.long, device=dev))
+    ok = F.render_rays(model, o, d, 2.0, 6.0, 16, 16, cond, view_id=(torch.arange(64) % 4).to(dev))
+    assert torch.isfinite(ok["rgb"]).all()
+    # codes that require grad are refused loudly (inputs carry no gradient, A.4) instead of silently getting None
+    with pytest.raises(NotImplementedError):
+        F.render_rays(model, o, d, 2.0, 6.0, 16, 16, cond.clone().requires_grad_(True), view_id=(torch.arange(64) % 4).to(dev))
+
+
+def test_raw_noise_kwarg_matches_oracle(F, cuda_device):
+    """SURVEY.md 8b signature: raw_noise is added to sigma_raw before the ReLU in both passes (A.5)."""
+    dev = cuda_device
+    pc, pf = O.init_params(0), O.init_params(1)
+    o, d = O.pinhole_rays(16, 16)
+    R, Nc, Nf = 256, 32, 32
+    g = torch.Generator().manual_seed(4)
+    u_s, u_f = torch.rand(R, Nc, generator=g), torch.rand(R, Nf, generator=g)
+    nz = (torch.randn(R, Nc, generator=g), torch.randn(R, Nc + Nf, generator=g))
+    with torch.no_grad():
+        ref = O.render_rays(pc, pf, o, d, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f, raw_noise=nz)
+        plain = O.render_rays(pc, pf, o, d, 2.0, 6.0, Nc, Nf, u_strat=u_s, u_fine=u_f)
+    assert (ref["rgb"] - plain["rgb"]).abs().max() > 1e-2                    # the noise matters (sigma ~ 0 at random init)
+    model = F.NerfModel(F.NerfNetwork.from_state_dict(pc, dev), F.NerfNetwork.from_state_dict(pf, dev))
+    with torch.no_grad():
+        out = F.render_rays(model, o.to(dev), d.to(dev), 2.0, 6.0, Nc, Nf, u_strat=u_s.to(dev), u_fine=u_f.to(dev),
+                            raw_noise=tuple(t.to(dev) for t in nz), precision="fp32")
+        img = F.render_image(model, o.to(dev), d.to(dev), 2.0, 6.0, Nc, Nf, chunk=100, u_strat=u_s.to(dev), u_fine=u_f.to(dev),
+                             raw_noise=tuple(t.to(dev) for t in nz), precision="fp32")
+    assert (out["rgb"].cpu() - ref["rgb"]).abs().max() <= 2e-4
+    assert (out["rgb0"].cpu() - ref["rgb0"]).abs().max() <= 2e-4
+    assert torch.equal(img["rgb"], out["rgb"])
+    with pytest.raises(ValueError):
+        F.render_rays(model, o.to(dev), d.to(dev), 2.0, 6.0, Nc, Nf, raw_noise=nz[0].to(dev))     # needs a pair
+    with torch.no_grad():                                                                        # single pass: a tensor
+        o1 = F.render_rays(model, o.to(dev), d.to(dev), 2.0, 6.0, Nc, 0, u_strat=u_s.to(dev), raw_noise=nz[0].to(dev), precision="fp32")
+        r1 = O.render_rays(pc, pf, o, d, 2.0, 6.0, Nc, 0, u_strat=u_s, raw_noise=(nz[0], None))
+    assert (o1["rgb"].cpu() - r1["rgb"]).abs().max() <= 2e-4

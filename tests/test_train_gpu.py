@@ -428,3 +428,114 @@ def test_allreduce_adam_world1_equals_adam(F, cuda_device):
             F.ops.allreduce_adam_step(ptrs.data_ptr(), world, off, p_got, m2, v2, t)
         tol = 0 if world == 1 else 1e-6
         assert (p_ref - p_got).abs().max() <= tol
+
+
+def test_render_rays_autograd_disp_and_raw_taps(F, cuda_device):
+    """a loss on disp / disp0 / the raw taps must produce gradients (they used to be dropped silently), and
+    a loss on the detached sample positions must raise."""
+    dev = cuda_device
+    pc, pf = O.init_params(0), O.init_params(1)
+    for p in (pc, pf):
+        p["alpha_linear.bias"] += 0.3
+    o, d = O.pinhole_rays(8, 12)
+    R, Nc, Nf = o.shape[0], 24, 24
+    g = torch.Generator().manual_seed(0)
+    u_s, u_f = torch.rand(R, Nc, generator=g), torch.rand(R, Nf, generator=g)
+    wr = torch.randn(R, Nc + Nf, 4, generator=g)
+    # oracle: same loss through autograd
+    qc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    qf = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    viewdirs, dnorm = O.ray_setup(d)
+    z_c = O.stratified(torch.full((R,), 2.0), torch.full((R,), 6.0), torch.linspace(0, 1, Nc), u_s)
+    raw_c = O.run_network(qc, o[:, None] + d[:, None] * z_c[..., None], viewdirs)
+    oc = O.raw2outputs(raw_c, z_c, dnorm)
+    z_f = O.sample_pdf(z_c, oc["weights"].detach(), u_f)["z_f"]
+    raw_f = O.run_network(qf, o[:, None] + d[:, None] * z_f[..., None], viewdirs)
+    of = O.raw2outputs(raw_f, z_f, dnorm)
+    loss_ref = (of["disp"] ** 2).mean() + 0.5 * oc["disp"].mean() + 1e-3 * (raw_f * wr).sum() + (of["depth"] * of["acc"]).mean()
+    loss_ref.backward()
+    model = F.NerfModel(F.NerfNetwork.from_state_dict(pc, dev), F.NerfNetwork.from_state_dict(pf, dev))
+    model.coarse.flat.requires_grad_(True)
+    model.fine.flat.requires_grad_(True)
+    out = F.render_rays(model, o.to(dev), d.to(dev), 2.0, 6.0, Nc, Nf, u_strat=u_s.to(dev), u_fine=u_f.to(dev), precision="fp32",
+                        return_taps=True)
+    loss = (out["disp"] ** 2).mean() + 0.5 * out["disp0"].mean() + 1e-3 * (out["raw_f"] * wr.to(dev)).sum() + (out["depth"] * out["acc"]).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * max(1.0, abs(loss_ref.item()))
+    for q, net in ((qc, model.coarse), (qf, model.fine)):
+        ref = _flat_grads(F, {k: v.grad for k, v in q.items()})
+        assert ref.abs().max() > 0
+        err = _rel_err(net.flat.grad.cpu(), ref)
+        assert err <= 3e-3, err
+    out = F.render_rays(model, o.to(dev), d.to(dev), 2.0, 6.0, Nc, Nf, u_strat=u_s.to(dev), u_fine=u_f.to(dev), precision="fp32",
+                        return_taps=True)
+    with pytest.raises(RuntimeError):
+        (out["z_std"].sum() + out["rgb"].sum()).backward()
+
+
+def _oracle_grads_chunked(pc, pf, o, d, tgt, u_s, u_f, Nc, Nf, chunk=512):
+    """A.10 gradients of the mean loss over R rays, accumulated over chunks of rays (the oracle's autograd graph of
+    4096 x 256 samples would need > 12 GB in one piece)."""
+    R = o.shape[0]
+    gc = gf = None
+    loss = 0.0
+    for s in range(0, R, chunk):
+        sl = slice(s, min(s + chunk, R))
+        n = sl.stop - sl.start
+        l, a, b = O.loss_and_grads(pc, pf, o[sl], d[sl], 2.0, 6.0, Nc, Nf, tgt[sl], u_strat=u_s[sl], u_fine=u_f[sl])
+        w = n / R
+        loss += w * l.item()
+        gc = {k: w * v for k, v in a.items()} if gc is None else {k: gc[k] + w * a[k] for k in a}
+        gf = {k: w * v for k, v in b.items()} if gf is None else {k: gf[k] + w * b[k] for k in b}
+    return loss, gc, gf
+
+
+@pytest.mark.parametrize("flip_free", [False, True])
+def test_cfg3_size_bf16_gradients_vs_oracle(F, cuda_device, flip_free):
+    """BASELINE configs[2] at its real size: 4096 rays drawn from the 800x800 frame (seed = rank 0), 64+128 samples, bf16
+    tape forward + tcgen05 backward, against the fp32 oracle's autograd.  Random init: cosine >= 0.995 per weight tensor
+    (ReLU-mask flips of the bf16 forward are the floor).  Flip-free network (weights x0.1, biases +-1):
+    <= 1e-2 relative per tensor -- what is left is bf16 rounding of dZ and of the activations."""
+    dev = cuda_device
+    R, Nc, Nf = 4096, 64, 128
+    pc, pf = O.init_params(0), O.init_params(1)
+    g = torch.Generator().manual_seed(34)
+    for p in (pc, pf):
+        if flip_free:
+            for k in p:
+                if k.endswith("weight") and not k.startswith(("alpha", "rgb")):
+                    p[k] = 0.1 * p[k]
+                if k.endswith("bias") and k.startswith(("pts", "views")):
+                    p[k] = (torch.randint(0, 2, p[k].shape, generator=g) * 2 - 1).float()
+        p["alpha_linear.bias"] += 0.3                 # visible density so that gradients are not dominated by the far sample
+    o_all, d_all = O.pinhole_rays(800, 800)
+    idx = torch.randperm(800 * 800, generator=torch.Generator().manual_seed(0))[:R]
+    o, d = o_all[idx].contiguous(), d_all[idx].contiguous()
+    gi = torch.Generator().manual_seed(0)
+    u_s, u_f = torch.rand(R, Nc, generator=gi), torch.rand(R, Nf, generator=gi)
+    tgt = torch.rand(R, 3, generator=torch.Generator().manual_seed(100))
+    loss_ref, gc, gf = _oracle_grads_chunked(pc, pf, o, d, tgt, u_s, u_f, Nc, Nf)
+    model = F.NerfModel(F.NerfNetwork.from_state_dict(pc, dev), F.NerfNetwork.from_state_dict(pf, dev))
+    model.coarse.flat.requires_grad_(True)
+    model.fine.flat.requires_grad_(True)
+    out = F.render_rays(model, o.to(dev), d.to(dev), 2.0, 6.0, Nc, Nf, u_strat=u_s.to(dev), u_fine=u_f.to(dev), precision="bf16")
+    loss = ((out["rgb"] - tgt.to(dev)) ** 2).mean() + ((out["rgb0"] - tgt.to(dev)) ** 2).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_ref) <= 2e-3
+    worst_cos, worst_rel = 1.0, 0.0
+    for name, net, ref in (("coarse", model.coarse, gc), ("fine", model.fine, gf)):
+        got = F.unflatten(net.flat.grad.cpu(), False)
+        for k, want in ref.items():
+            if want.norm() < 1e-12:
+                continue
+            cos = torch.nn.functional.cosine_similarity(got[k].reshape(-1), want.reshape(-1), dim=0).item()
+            rel = _rel_err(got[k], want)
+            worst_cos, worst_rel = min(worst_cos, cos), max(worst_rel, rel)
+            print(f"cfg3 {'flip-free' if flip_free else 'random-init'} {name} {k}: cosine {cos:.5f} rel {rel:.3e}")
+            if flip_free:
+                assert rel <= 1e-2, (name, k, rel)
+            elif k.endswith("weight"):
+                assert cos >= 0.995, (name, k, cos)
+            else:
+                assert cos >= 0.99, (name, k, cos)
+    print(f"cfg3 size: worst cosine {worst_cos:.5f}, worst rel {worst_rel:.3e}")
