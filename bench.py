@@ -9,9 +9,15 @@ ray setup, stratified sampling, coarse MLP, compositing, importance sampling, fi
 
   value : rays/s with rays already resident in HBM (device-timed, max over ranks)
   e2e   : the same through the public API (fashion_nerf_b200.render_rays) with HOST pinned
-          buffers: H2D of rays_o/rays_d and D2H of rgb/disp/acc/depth inside the timed region
+          buffers: H2D of rays_o/rays_d and D2H of rgb/disp/acc/depth inside the timed region; the two
+          uniform tensors (492 MB per frame) are generated ON THE DEVICE inside the timed region
   roofline : the fine-pass tcgen05 MLP launch (the dominant kernel), timed live with CUDA events
           recorded inside fnerf_render_rays around the launch, against the measured bf16 peak
+  roofline_stages (N=1): the memory-bound stage kernels standalone at R = 2^20 rays against the measured HBM peak
+  train : BASELINE configs[2], the data-parallel training step (4096 rays/GPU, bf16 tape forward + tcgen05 backward, ONE
+          gradient all-reduce per step) in every all-reduce mode the box offers
+  strong : BASELINE configs[3], one 1920x1080 frame at 256+768 samples split over the N ranks
+  fp32_path (N=1): the fp32 SIMT path of configs[1] on a slice of the frame
   cpu_baseline : the fp32 PyTorch oracle on a bounded sample (4096 rays of the same frame)
 
 `--impl reference` times the CPU oracle alone (the reference ships no code, so the oracle port is
@@ -38,10 +44,14 @@ N_C, N_F = 64, 128
 NEAR, FAR = 2.0, 6.0
 FLOP_PER_SAMPLE = 1_186_816          # un-padded 593,408 MAC
 FLOP_PER_RAY = FLOP_PER_SAMPLE * (N_C + N_C + N_F)
+TRAIN_FLOP_PER_RAY = 893_190_144     # forward + dgrad + wgrad, 256 network evaluations per ray
+TRAIN_RAYS = 4096                    # canonical N_rand (configs[2])
+GRAD_BYTES = 4_766_752               # 1,191,688 fp32 gradients all-reduced per step
 # dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass k_mlp_tc launch of THIS workload (640,000 rays x 192
-# samples) from one `ncu --set full` capture of `bench.py --steps 1 --warmup 3` (profiles/r1_bench_fine_launch_ncu_key_metrics.txt);
-# the algorithmic HBM bytes of that launch are 20 B/sample = 2,457,600,000
+# samples) from one `ncu --set full` capture of `bench.py --steps 1 --warmup 3`; a STATIC figure copied from profiles/
+# (the driver's run is not under ncu), next to the algorithmic 20 B/sample = 2,457,600,000
 NCU_FINE_LAUNCH_DRAM_BYTES = 542_652_160 + 1_917_181_000
+NCU_TRAFFIC_SOURCE = "static, from profiles/r1_bench_fine_launch_ncu_key_metrics.txt (dram read + write of this launch, ncu --set full); not measured in this run"
 CPU_SAMPLE_RAYS = 4096
 WORKLOAD = ("single-B200 full-frame 800x800 render per GPU (BASELINE configs[1]); view r of N per rank, "
             "random-init 8x256 NeRF MLPs (seeds 0/1), L=10/4 PE")
@@ -74,6 +84,7 @@ class ClockSampler:
                                          stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        return self
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -110,6 +121,10 @@ class ClockSampler:
         return out
 
 
+def _clk(c):
+    return {"sm_mhz": c["sm_mhz"], "sm_max_mhz": c["sm_max_mhz"], "reasons": c["reasons"]}
+
+
 def cpu_oracle_rate(steps: int, warmup: int):
     """Rays/s of the fp32 PyTorch oracle on CPU_SAMPLE_RAYS rays of the 800x800 frame."""
     from oracle import nerf_oracle as O
@@ -133,13 +148,15 @@ def cpu_oracle_rate(steps: int, warmup: int):
 
 
 def run_reference(args):
+    """The reference arm: the oracle port on the host cores of rank 0, honouring --steps / --warmup.  A step is a
+    bounded sample of the workload (4096 rays of the frame, ~2 s on 16 cores), so K = 10, W = 3 ends within a minute."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     rate, cores, times = cpu_oracle_rate(steps, warmup)
-    val = rate / 1e6
-    sample = f"{CPU_SAMPLE_RAYS} rays evenly spread over the 800x800 frame, 64+128 samples, fp32 PyTorch oracle"
+    val = CPU_SAMPLE_RAYS / statistics.mean(times) / 1e6            # mean over exactly K timed steps
+    sample = f"{CPU_SAMPLE_RAYS} rays evenly spread over the 800x800 frame per step, 64+128 samples, fp32 PyTorch oracle"
     print(json.dumps({
         "impl": "reference", "metric": "render throughput, 64+128 samples, 8x256 MLP", "value": val,
         "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
@@ -148,10 +165,241 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "rays_per_gpu_per_step": H * W, "N_samples": N_C, "N_importance": N_F,
                    "reference_sample_rays_per_step": CPU_SAMPLE_RAYS,
                    "parallelism": "host cores of rank 0 only"},
-        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample,
+                         "best_step_value": rate / 1e6},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """Rank / device plumbing shared by the bench sections."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, reps: int, warm: int = 1) -> float:
+        """ms per call of fn(): `warm` untimed calls, then `reps` calls between CUDA events, barrier + synchronize on
+        both sides, max over ranks."""
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / reps
+
+
+def bench_stages(F, cx: Ctx, peaks):
+    """HBM rooflines of the memory-bound stage kernels, standalone at R = 2^20 rays (working sets of 0.5-26 GB >> the
+    126 MB L2), SURVEY.md 8(d) algorithmic bytes per ray, CUDA events, clocks sampled during the region."""
+    dev = cx.dev
+    R = 1 << 20
+    peak = peaks["hbm_gbs"]
+    out = {}
+    sampler = ClockSampler(cx.local_rank).start()
+    g = torch.Generator(device=dev).manual_seed(0)
+
+    def add(name, kernel, bytes_per_ray, fn, reps=5):
+        ms = cx.timed(fn, reps, warm=2)
+        gbs = bytes_per_ray * R / (ms * 1e-3) / 1e9
+        out[name] = {"kernel": kernel, "rays": R, "bytes_per_ray": bytes_per_ray, "ms": round(ms, 4),
+                     "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+
+    near, far = torch.full((R,), NEAR, device=dev), torch.full((R,), FAR, device=dev)
+    dn = 1.0 + torch.rand(R, device=dev, generator=g)
+    for n in (64, 256):
+        t_vals = torch.linspace(0.0, 1.0, n).to(dev)
+        u = torch.rand(R, n, device=dev, generator=g)
+        add(f"stratified_{n}", "k_stratified_v4", 8 * n + 8, lambda: F.ops.stratified(near, far, t_vals, u))
+        del u
+    for nc, nf in ((64, 128), (256, 768)):
+        t_vals = torch.linspace(0.0, 1.0, nc).to(dev)
+        z_c = F.ops.stratified(near, far, t_vals, torch.rand(R, nc, device=dev, generator=g))
+        w_c = torch.rand(R, nc, device=dev, generator=g)
+        u = torch.rand(R, nf, device=dev, generator=g)
+        add(f"importance_{nc}_{nf}", "k_importance_*", 8 * nc + 4 * nf + 4 * (nc + nf) + 4,
+            lambda: F.ops.importance(z_c, w_c, u, want_idx=False))
+        del z_c, w_c, u
+    for S in (64, 192, 1024):
+        raw = torch.randn(R, S, 4, device=dev, generator=g)
+        z = torch.cumsum(torch.rand(R, S, device=dev, generator=g), -1) * (4.0 / S) + 2.0      # ascending depths in [2, 6]
+        add(f"composite_fwd_{S}", "k_composite_fwd*", 24 * S + 36, lambda: F.ops.composite_fwd(raw, z, dn))
+        g_rgb = torch.randn(R, 3, device=dev, generator=g)
+        add(f"composite_bwd_{S}", "k_composite_bwd*", 36 * S + 24, lambda: F.ops.composite_bwd(raw, z, dn, g_rgb))
+        del raw, z, g_rgb
+    torch.cuda.empty_cache()
+    return {"peak_gbs": peak, "peak_kind": f"hbm copy, {peaks['source']}", "stages": out, "clocks": _clk(sampler.stop()),
+            "method": "R = 2^20 rays per launch, 2 warm-up + 5 timed launches, CUDA events; torch allocates the outputs inside the timed call"}
+
+
+def bench_train(F, cx: Ctx, peaks, steps: int):
+    """BASELINE configs[2]: the data-parallel training step, 4096 rays per GPU drawn from the 800x800 frame (seed = rank,
+    targets seed 100 + rank), 64+128 samples, bf16 tape forward + tcgen05 backward, ONE gradient all-reduce
+    (4.77 MB) per step.  Every all-reduce mode the box offers is timed from the same initial state; their reduce + Adam
+    results are compared on IDENTICAL local gradients."""
+    from fashion_nerf_b200.train import Trainer
+    dev, world, rank = cx.dev, cx.world, cx.rank
+    o_all, d_all = F.pinhole_rays(H, W)
+    idx = torch.randperm(H * W, generator=torch.Generator().manual_seed(rank))[:TRAIN_RAYS]
+    o, d = o_all[idx].contiguous().to(dev), d_all[idx].contiguous().to(dev)
+    tgt = torch.rand(TRAIN_RAYS, 3, generator=torch.Generator().manual_seed(100 + rank)).to(dev)
+    g = torch.Generator().manual_seed(rank)
+    u_s, u_f = torch.rand(TRAIN_RAYS, N_C, generator=g).to(dev), torch.rand(TRAIN_RAYS, N_F, generator=g).to(dev)
+    modes = [("single", None)] if world == 1 else [("nccl", False), ("p2p", True), ("nvls", "nvls")]
+    peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+    default_mode = Trainer(F.NerfModel.random(dev)).mode
+    rec = {"workload": "BASELINE configs[2]: data-parallel training step, 4096 rays/GPU from the 800x800 frame, 64+128 samples, "
+                       "bf16 tape forward + tcgen05 dgrad/wgrad, one 4.77 MB gradient all-reduce, Adam, re-pack",
+           "rays_per_gpu": TRAIN_RAYS, "steps": steps, "warmup": 3, "flop_per_ray": TRAIN_FLOP_PER_RAY,
+           "allreduce_bytes": GRAD_BYTES if world > 1 else 0, "default_mode": default_mode, "peak_tflops": peak,
+           "peak_kind": f"sustained bf16, {peaks['source']}", "modes": {}}
+    trainers, unavailable = {}, {}
+    for name, flag in modes:
+        try:
+            trainers[name] = Trainer(F.NerfModel.random(dev), fused_allreduce=flag)
+        except Exception as e:                      # e.g. no multicast mapping -> no NVLS on this box (agreed over the ranks)
+            unavailable[name] = f"{type(e).__name__}: {e}"[:160]
+    # ---- parity of the reduce + Adam paths on identical local gradients --------------------------------------------
+    first = next(iter(trainers.values()))
+    m0 = first.model
+    fc = m0.coarse.flat.detach().requires_grad_(True)
+    ff = m0.fine.flat.detach().requires_grad_(True)
+    m0.coarse.flat, m0.fine.flat = fc, ff
+    out = F.render_rays(m0, o, d, NEAR, FAR, N_C, N_F, u_strat=u_s, u_fine=u_f)
+    (((out["rgb"] - tgt) ** 2).mean() + ((out["rgb0"] - tgt) ** 2).mean()).backward()
+    m0.coarse.flat, m0.fine.flat = fc.detach(), ff.detach()
+    local_grad = torch.cat([fc.grad, ff.grad]).clone()
+    del out
+    after = {}
+    for name, tr in trainers.items():
+        tr.flat_grad.copy_(local_grad)
+        tr.reduce_and_update()
+        torch.cuda.synchronize()
+        after[name] = torch.cat([tr.model.coarse.flat, tr.model.fine.flat]).clone()
+    base = after.get("nccl", next(iter(after.values())))
+    # ---- timing, every mode from the state the parity step left (identical across modes up to the last bit) ---------
+    for name, tr in trainers.items():
+        def one_step():
+            return tr.step(o, d, tgt, NEAR, FAR, N_C, N_F, u_strat=u_s, u_fine=u_f)
+        for _ in range(3):
+            one_step()
+        cx.barrier()
+        tr.events = []
+        sampler = ClockSampler(cx.local_rank).start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = one_step()
+        e1.record()
+        cx.barrier()
+        clocks = sampler.stop()
+        ms = cx.max_over_ranks(e0.elapsed_time(e1)) / steps
+        red_us = cx.max_over_ranks(1e3 * statistics.mean(a.elapsed_time(b) for a, b in tr.events))
+        tr.events = None
+        chk = torch.cat([tr.model.coarse.flat, tr.model.fine.flat]).view(torch.int32).to(torch.int64).sum().reshape(1)
+        same = True
+        if world > 1:
+            allc = [torch.empty_like(chk) for _ in range(world)]
+            cx.dist.all_gather(allc, chk)
+            same = all(bool(torch.equal(allc[0], c)) for c in allc)
+        tflops = TRAIN_RAYS * TRAIN_FLOP_PER_RAY / (ms * 1e-3) / 1e12
+        rec["modes"][name] = {"ms_per_step": round(ms, 4), "allreduce_adam_us": round(red_us, 2),
+                              "algorithmic_tflops": round(tflops, 1), "frac": round(tflops / peak, 4),
+                              "Mrays_s_job": round(world * TRAIN_RAYS / (ms * 1e-3) / 1e6, 4),
+                              "replicas_identical": bool(same), "loss": float(res["loss"]),
+                              "max_abs_param_vs_nccl": float((after[name] - base).abs().max()),
+                              "clocks": _clk(clocks)}
+    for name, why in unavailable.items():
+        rec["modes"][name] = {"unavailable": why}
+    d_name = default_mode if default_mode in rec["modes"] and "ms_per_step" in rec["modes"][default_mode] else next(iter(trainers))
+    dm = rec["modes"][d_name]
+    rec.update({"ms_per_step": dm["ms_per_step"], "algorithmic_tflops": dm["algorithmic_tflops"], "frac": dm["frac"],
+                "allreduce_adam_us": {k: v["allreduce_adam_us"] for k, v in rec["modes"].items() if "allreduce_adam_us" in v},
+                "replicas_identical": all(v.get("replicas_identical", True) for v in rec["modes"].values()),
+                "max_abs_fused_vs_nccl": max([v["max_abs_param_vs_nccl"] for k, v in rec["modes"].items()
+                                              if k in ("p2p", "nvls") and "max_abs_param_vs_nccl" in v] or [0.0]),
+                "clocks": dm["clocks"]})
+    del trainers
+    torch.cuda.empty_cache()
+    return rec
+
+
+def bench_strong(F, cx: Ctx, model):
+    """BASELINE configs[3]: ONE 1920x1080 frame at 256 coarse + 768 fine samples, the flat ray list split into N
+    contiguous shards (no gather in the timed region), max over ranks.  Rank 0 also renders the whole frame alone, so
+    the efficiency against N = 1 comes from this run, on this box."""
+    dev, world, rank = cx.dev, cx.world, cx.rank
+    HH, WW, nc, nf = 1080, 1920, 256, 768
+    o_all, d_all = F.pinhole_rays(HH, WW)
+    R = o_all.shape[0]
+    lo, hi = R * rank // world, R * (rank + 1) // world
+    chunk = 1 << 17                                           # 131,072 rays x 1024 samples x 16 B = 2.1 GB of raw per chunk
+    g = torch.Generator(device=dev).manual_seed(7)
+
+    def render(o, d):
+        n = o.shape[0]
+        u_s = torch.rand(min(n, chunk), nc, device=dev, generator=g)      # one chunk's worth of uniforms, reused per chunk
+        u_f = torch.rand(min(n, chunk), nf, device=dev, generator=g)
+        acc = []
+        with torch.no_grad():
+            for s in range(0, n, chunk):
+                e = min(s + chunk, n)
+                acc.append(F.render_rays(model, o[s:e], d[s:e], NEAR, FAR, nc, nf, u_strat=u_s[: e - s], u_fine=u_f[: e - s])["rgb"])
+        return acc
+
+    o, d = o_all[lo:hi].contiguous().to(dev), d_all[lo:hi].contiguous().to(dev)
+    ms_shard = cx.timed(lambda: render(o, d), reps=2, warm=1)
+    rec = {"workload": "BASELINE configs[3]: one 1920x1080 frame, 256 coarse + 768 fine samples per ray, ray-sharded over the ranks",
+           "rays": R, "n_gpus": world, "ms": round(ms_shard, 3), "Mrays_s": round(R / (ms_shard * 1e-3) / 1e6, 4),
+           "flop_per_ray": FLOP_PER_SAMPLE * (nc + nc + nf), "rays_per_chunk": chunk}
+    rec["tflops_per_gpu"] = round(R * rec["flop_per_ray"] / (ms_shard * 1e-3) / 1e12 / world, 1)
+    if world > 1:
+        t = torch.zeros(1, device=dev, dtype=torch.float64)
+        if rank == 0:
+            o1, d1 = o_all.to(dev), d_all.to(dev)
+            render(o1[:chunk], d1[:chunk])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            render(o1, d1)
+            e1.record()
+            torch.cuda.synchronize()
+            t[0] = e0.elapsed_time(e1)
+            del o1, d1
+        cx.dist.all_reduce(t, op=cx.dist.ReduceOp.MAX)
+        ms_one = float(t.item())
+        rec.update({"ms_n1_same_run": round(ms_one, 3), "efficiency_vs_N1": round(ms_one / world / ms_shard, 4)})
+    else:
+        rec["efficiency_vs_N1"] = 1.0
+    torch.cuda.empty_cache()
+    return rec
 
 
 def main():
@@ -162,25 +410,18 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-render", action="store_true", help="skip the train / strong / stages / fp32 sections")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch.distributed as dist
     import fashion_nerf_b200 as F
     from fashion_nerf_b200 import render as R_
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    cx = Ctx()
+    rank, world, dev = cx.rank, cx.world, cx.dev
     steps, warmup = args.steps, max(args.warmup, 3)
-    F.load_library()
+    lib = F.load_library()
 
     # ---- inputs: rank r renders view r of `world` (weak scaling), weights replicated -------------
     model = F.NerfModel.random(dev)
@@ -192,6 +433,7 @@ def main():
     o_d, d_d, u_s, u_f = o_h.to(dev), d_h.to(dev), u_s_h.to(dev), u_f_h.to(dev)
     out_pin = {k: torch.empty(s, dtype=torch.float32).pin_memory()
                for k, s in (("rgb", (R, 3)), ("disp", (R,)), ("acc", (R,)), ("depth", (R,)))}
+    dev_gen = torch.Generator(device=dev).manual_seed(1000 + rank)
 
     def step_resident():
         with torch.no_grad():
@@ -202,22 +444,12 @@ def main():
         with torch.no_grad():
             o = o_pin.to(dev, non_blocking=True)
             d = d_pin.to(dev, non_blocking=True)
-            out = F.render_rays(model, o, d, NEAR, FAR, N_C, N_F, u_strat=u_s, u_fine=u_f, precision=args.precision)
+            us = torch.rand(R, N_C, device=dev, generator=dev_gen)          # the caller's jitter, drawn on the device each frame
+            uf = torch.rand(R, N_F, device=dev, generator=dev_gen)
+            out = F.render_rays(model, o, d, NEAR, FAR, N_C, N_F, u_strat=us, u_fine=uf, precision=args.precision)
             for k, buf in out_pin.items():
                 buf.copy_(out[k], non_blocking=True)
         return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     # ---- resident-input timing (value) + live per-launch timing of the dominant kernel ------------
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
@@ -226,9 +458,9 @@ def main():
             e.record()                       # materialise the cudaEvent_t handles
     for _ in range(warmup):
         step_resident()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    cx.barrier()
+    sampler = ClockSampler(cx.local_rank).start()
+    launches0 = int(lib.fnerf_launch_count())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
@@ -236,30 +468,41 @@ def main():
         step_resident()
     e1.record()
     R_.set_profile_events(None)
-    barrier()
+    launches = int(lib.fnerf_launch_count()) - launches0
+    cx.barrier()
     clocks = sampler.stop()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = cx.max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / steps
     value = world * R / (ms_step * 1e-3) / 1e6
     fine_ms = statistics.mean(r[2].elapsed_time(r[3]) for r in evs)
     coarse_ms = statistics.mean(r[0].elapsed_time(r[1]) for r in evs)
 
     # ---- end-to-end timing through the public API with host buffers --------------------------------
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    e0.record()
-    for _ in range(steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / steps
+    ms_e2e = cx.timed(step_e2e, reps=steps, warm=2)
     e2e_value = world * R / (ms_e2e * 1e-3) / 1e6
     h2d = o_pin.numel() * 4 + d_pin.numel() * 4
     d2h = sum(b.numel() * 4 for b in out_pin.values())
 
+    peaks = _peaks()
+    extra = {}
+    if not args.only_render and args.precision == "bf16":
+        extra["train"] = bench_train(F, cx, peaks, steps=max(steps, 20))
+        extra["strong"] = bench_strong(F, cx, model)
+        if world == 1:
+            extra["roofline_stages"] = bench_stages(F, cx, peaks)
+            # the fp32 SIMT path of configs[1] ("bf16 tcgen05 path vs fp32 CUDA path") on 1/8 of the frame (~1 s per pass)
+            n32 = R // 8
+            g32 = torch.Generator(device=dev).manual_seed(5)
+            us32, uf32 = torch.rand(n32, N_C, device=dev, generator=g32), torch.rand(n32, N_F, device=dev, generator=g32)
+
+            def step_fp32():
+                with torch.no_grad():
+                    F.render_rays(model, o_d[:n32], d_d[:n32], NEAR, FAR, N_C, N_F, u_strat=us32, u_fine=uf32, precision="fp32")
+            ms32 = cx.timed(step_fp32, reps=2, warm=1)
+            extra["fp32_path"] = {"value": n32 / (ms32 * 1e-3) / 1e6, "unit": "Mrays/s", "sample": f"first {n32} rays of the frame (1/8), 64+128 samples",
+                                  "ms": ms32, "tflops_fp32": n32 * FLOP_PER_RAY / (ms32 * 1e-3) / 1e12}
+
     if rank == 0:
-        peaks = _peaks()
         use_bf16 = args.precision == "bf16"
         fine_flop = R * (N_C + N_F) * FLOP_PER_SAMPLE
         achieved = fine_flop / (fine_ms * 1e-3) / 1e12
@@ -270,7 +513,7 @@ def main():
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "peak_kind": f"sustained, {peaks['source']}",
                     "traffic": NCU_FINE_LAUNCH_DRAM_BYTES if (use_bf16 and R == 640000) else None,
-                    "traffic_source": "profiles/r1_bench_fine_launch_ncu_key_metrics.txt (dram read + write of this launch, ncu --set full)",
+                    "traffic_source": NCU_TRAFFIC_SOURCE,
                     "algorithmic_hbm_bytes": R * (N_C + N_F) * 20,
                     "launch_ms": fine_ms, "coarse_launch_ms": coarse_ms,
                     "kernel_share_of_step": (fine_ms + coarse_ms) / ms_step,
@@ -284,11 +527,15 @@ def main():
                        "l2_policy": "inputs+intermediates per step (~2.7 GB) exceed the 126 MB L2",
                        "parallelism": f"ray-sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e},
-            "gpu_launches": 7 * steps,
+                    "ms_per_step": ms_e2e,
+                    "uniforms": f"u_strat / u_fine ({R * (N_C + N_F) * 4} B per step) are drawn on the device inside the timed "
+                                "region (torch.rand), not copied from the host"},
+            "gpu_launches": launches,
+            "gpu_launches_source": "fnerf_launch_count(): kernels libfnerf.so launched inside the timed region of `value`",
             "roofline": roofline,
-            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+            "clocks": _clk(clocks),
         }
+        line.update(extra)
         if not args.no_cpu_baseline and world == 1:
             rate, cores, _ = cpu_oracle_rate(steps=2, warmup=1)
             line["cpu_baseline"] = {"value": rate / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
@@ -296,8 +543,8 @@ def main():
                                               "64+128 samples, fp32 PyTorch oracle, best of 2 after 1 warm-up"}
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -48,6 +48,7 @@ class RenderArgs(ctypes.Structure):
 SIGNATURES = {
     "fnerf_abi_version": (c_int, []),
     "fnerf_last_error": (c_char_p, []),
+    "fnerf_launch_count": (c_int64, []),
     "fnerf_param_count": (c_int64, [c_int]),
     "fnerf_packed_bytes": (c_int64, [c_int]),
     "fnerf_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),

@@ -2,9 +2,13 @@
 // orchestration (A.9).  Everything here only enqueues work on the caller's stream.
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace fnerf {
+
+static std::atomic<int64_t> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 char* error_buffer() {
   static thread_local char buf[512] = {0};
@@ -48,6 +52,7 @@ using namespace fnerf;
 extern "C" {
 
 int fnerf_abi_version(void) { return FNERF_ABI_VERSION; }
+int64_t fnerf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* fnerf_last_error(void) { return error_buffer(); }
 
 int64_t fnerf_param_count(int cond) { return flat_count(cond ? 1 : 0); }

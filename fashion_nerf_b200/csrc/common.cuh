@@ -13,7 +13,12 @@ namespace fnerf {
 char* error_buffer();
 int set_error(int code, const char* fmt, ...);
 
-inline int check_launch(const char* what) {
+// process-wide count of kernels this library has launched (fnerf_launch_count(); bench.py reports it as gpu_launches)
+void note_launches(int n);
+
+// called after every kernel launch (n = kernels launched since the previous call)
+inline int check_launch(const char* what, int n = 1) {
+  note_launches(n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error((int)e, "%s: %s", what, cudaGetErrorString(e));
   return 0;

@@ -126,6 +126,7 @@ static void gemm(const GemmArgs& g, cudaStream_t s) {
   dim3 grid((g.J + kBN - 1) / kBN, (g.I + kBM - 1) / kBM, 1);
   if (EPI == EPI_WGRAD) grid.z = (unsigned)((g.K + g.k_split - 1) / g.k_split);
   k_sgemm<TA, TB, EPI><<<grid, kGemmThreads, 0, s>>>(g);
+  note_launches(1);
 }
 
 // column sums of dZ[M,N] (ld) added into out[N] (bias gradients)
@@ -142,6 +143,7 @@ static void colsum(const float* dz, int64_t ld, int64_t M, int N, float* out, cu
   const int64_t rpb = 512;
   dim3 grid((N + 127) / 128, (unsigned)((M + rpb - 1) / rpb));
   k_colsum<<<grid, 128, 0, s>>>(dz, ld, M, N, out, rpb);
+  note_launches(1);
 }
 
 // encodings (A.3) of a chunk of samples into the concatenated layer inputs:
@@ -225,6 +227,7 @@ int launch_mlp_bwd_fp32(const MlpArgs& a, const float* g_raw, float* flat_grad, 
       const int64_t threads = mc * 3;
       k_encode_chunk<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a.rays_o, a.rays_d, a.viewdirs, a.z,
           cond ? a.cond_proj : nullptr, a.cond_index, a.C, (int)a.S, m0, mc, X5, in5, Xv, inv);
+      note_launches(1);
     }
     // ---- forward recompute -------------------------------------------------------------------------
     auto fwd = [&](const float* X, int64_t ldx, int K, const float* W, int N, const float* bias, int relu, float* Y, int64_t ldy) {
@@ -289,7 +292,7 @@ int launch_mlp_bwd_fp32(const MlpArgs& a, const float* g_raw, float* flat_grad, 
     wgrad(dz, kW, kW, X5, in5, kPE, gw(0), kPE);
     colsum(dz, kW, mc, kW, gb(0), s);
   }
-  return check_launch("mlp_bwd");
+  return check_launch("mlp_bwd", 0);
 }
 
 }  // namespace fnerf

@@ -124,7 +124,7 @@ int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s) {
   }
   k_pack_simt<<<dim3((unsigned)((nmax + 255) / 256), 10), 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecCOffset), cond);
   k_pack_bf16_T<<<dim3(kNumChunksT, 4), 256, 0, s>>>(flat, p + sec_e_offset(cond), cond);
-  return check_launch("pack_weights");
+  return check_launch("pack_weights", 4);
 }
 
 int launch_unpack(const void* packed, float* flat, int cond, cudaStream_t s) {

@@ -80,6 +80,7 @@ class Trainer:
         self.symm = None
         self.nvls = False
         self.flat_grad = None
+        self.events = None                        # profiling hook of reduce_and_update()
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.world = world
         if world > 1 and (fused_allreduce or (fused_allreduce is None and world <= 4)) and model.device.type == "cuda":
@@ -130,36 +131,56 @@ class Trainer:
                     g[self.n_c:].copy_(ff.grad)
                 else:
                     g[self.n_c:].zero_()
-            self.opt.t += 1
-            if self.symm is not None:
-                # every rank's gradients are in its symmetric buffer: barrier, then each rank sums all peers' buffers over
-                # NVLink inside the Adam kernel (same rank order everywhere -> identical replicas), barrier again so nobody
-                # overwrites its buffer while a peer still reads it
-                from . import ops
-                o = self.opt
-                self.symm.barrier(channel=0)
-                if self.nvls:
-                    ops.multimem_allreduce(self.symm.multicast_ptr, self.symm.rank, self.symm.world_size, g.numel(), g.device)
-                    self.symm.barrier(channel=1)
-                    sc = 1.0 / self.symm.world_size
-                    self.opt.apply(m.coarse.flat, g[:self.n_c], 0, sc)
-                    if not self.shared:
-                        self.opt.apply(m.fine.flat, g[self.n_c:], self.n_c, sc)
-                    m.repack()
-                    return {"loss": loss.detach(), "psnr": -10.0 * torch.log10(loss_f.detach())}
+        self.reduce_and_update()
+        return {"loss": loss.detach(), "psnr": -10.0 * torch.log10(loss_f.detach())}
+
+    @torch.no_grad()
+    def reduce_and_update(self) -> None:
+        """The data-parallel half of a step, on whatever local gradients `self.flat_grad` holds: mean over the ranks (the
+        ONE collective of the system), Adam on the fp32 master parameters, re-pack of the kernel blobs.
+        `self.events`, when set to a list, receives one (start, stop) CUDA-event pair around reduce + Adam per call."""
+        m, g, o = self.model, self.flat_grad, self.opt
+        ev = None
+        if self.events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        o.t += 1
+        if self.symm is not None:
+            # every rank's gradients are in its symmetric buffer: barrier, then each rank sums all peers' buffers over
+            # NVLink inside the Adam kernel (same rank order everywhere -> identical replicas), barrier again so nobody
+            # overwrites its buffer while a peer still reads it
+            from . import ops
+            self.symm.barrier(channel=0)
+            if self.nvls:
+                ops.multimem_allreduce(self.symm.multicast_ptr, self.symm.rank, self.symm.world_size, g.numel(), g.device)
+                self.symm.barrier(channel=1)
+                sc = 1.0 / self.symm.world_size
+                o.apply(m.coarse.flat, g[:self.n_c], 0, sc)
+                if not self.shared:
+                    o.apply(m.fine.flat, g[self.n_c:], self.n_c, sc)
+            else:
                 ops.allreduce_adam_step(self.symm.buffer_ptrs_dev, self.symm.world_size, 0, m.coarse.flat, o.m[:self.n_c],
                                         o.v[:self.n_c], o.t, lr=o.lr, betas=(o.b1, o.b2), eps=o.eps)
                 if not self.shared:
                     ops.allreduce_adam_step(self.symm.buffer_ptrs_dev, self.symm.world_size, self.n_c, m.fine.flat,
                                             o.m[self.n_c:], o.v[self.n_c:], o.t, lr=o.lr, betas=(o.b1, o.b2), eps=o.eps)
                 self.symm.barrier(channel=1)
-            else:
-                allreduce_mean_(g, self.group)
-                self.opt.apply(m.coarse.flat, g[:self.n_c], 0)
-                if not self.shared:
-                    self.opt.apply(m.fine.flat, g[self.n_c:], self.n_c)
-            m.repack()
-        return {"loss": loss.detach(), "psnr": -10.0 * torch.log10(loss_f.detach())}
+        else:
+            allreduce_mean_(g, self.group)
+            o.apply(m.coarse.flat, g[:self.n_c], 0)
+            if not self.shared:
+                o.apply(m.fine.flat, g[self.n_c:], self.n_c)
+        if ev is not None:
+            ev[1].record()
+            self.events.append(ev)
+        m.repack()
+
+    @property
+    def mode(self) -> str:
+        """How this trainer sums gradients over the ranks: 'single' | 'nccl' | 'p2p' (fused one-shot kernel) | 'nvls'."""
+        if self.world <= 1:
+            return "single"
+        return "nccl" if self.symm is None else ("nvls" if self.nvls else "p2p")
 
 
 def psnr_from_mse(mse: float) -> float:
