@@ -115,7 +115,7 @@ k_composite_fwd(const float4* __restrict__ raw, const float* __restrict__ z,
 // Register-resident variant for S <= 32*NB (NB <= 8): every load of the ray is issued before the first
 // scan step (NB float4 + NB floats in flight per lane), which is what an HBM-bound kernel needs; the
 // software-pipelined kernel above keeps only one 32-sample block in flight per warp.
-template <int NB>
+template <int NB, bool kHasNoise>
 __global__ void __launch_bounds__(kCompWarps * 32)
 k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
                     const float* __restrict__ dnorm, const float* __restrict__ noise, float* __restrict__ rgb_out,
@@ -136,7 +136,7 @@ k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
       zv[b] = 0.f;
       if (i < S) {
         rv[b] = ldg_stream4(rawr + i); zv[b] = ldg_stream(zr + i);
-        if (noise != nullptr) rv[b].w += ldg_stream(noise + r * S + i);     // sigma = raw[...,3] + raw_noise (A.5)
+        if (kHasNoise) rv[b].w += ldg_stream(noise + r * S + i);     // sigma = raw[...,3] + raw_noise (A.5)
       }
     }
     const float dn = dnorm[r];
@@ -197,12 +197,14 @@ int launch_composite_fwd(const float* raw, const float* z, const float* dnorm, c
   if (S <= 256) {
     const float4* raw4 = (const float4*)raw;
     const unsigned g = (unsigned)blocks, t = kCompWarps * 32;
+#define FN_FWD(NB) do { if (noise) k_composite_fwd_reg<NB, true><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); \
+                        else k_composite_fwd_reg<NB, false><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); } while (0)
     switch ((S + 31) / 32) {
-      case 1: k_composite_fwd_reg<1><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
-      case 2: k_composite_fwd_reg<2><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
-      case 3: case 4: k_composite_fwd_reg<4><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
-      case 5: case 6: k_composite_fwd_reg<6><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
-      default: k_composite_fwd_reg<8><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); break;
+      case 1: FN_FWD(1); break;
+      case 2: FN_FWD(2); break;
+      case 3: case 4: FN_FWD(4); break;
+      case 5: case 6: FN_FWD(6); break;
+      default: FN_FWD(8); break;
     }
     return check_launch("composite_fwd");
   }
@@ -311,7 +313,7 @@ k_composite_bwd(const float4* __restrict__ raw, const float* __restrict__ z,
 // Register-resident backward for S <= 32*NB: raw and z are read ONCE (all loads up front), the forward
 // scan keeps alpha / T / w*v per block in registers, the reverse scan writes g_raw.  Same arithmetic
 // as k_composite_bwd above.
-template <int NB>
+template <int NB, bool kHasNoise>
 __global__ void __launch_bounds__(kCompWarps * 32)
 k_composite_bwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
                     const float* __restrict__ dnorm, const float* __restrict__ noise, const float* __restrict__ g_rgb,
@@ -332,7 +334,7 @@ k_composite_bwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
       zv[b] = 0.f;
       if (i < S) {
         rv[b] = ldg_stream4(rawr + i); zv[b] = ldg_stream(zr + i);
-        if (noise != nullptr) rv[b].w += ldg_stream(noise + r * S + i);
+        if (kHasNoise) rv[b].w += ldg_stream(noise + r * S + i);
       }
     }
     const float dn = dnorm[r];
@@ -411,12 +413,14 @@ int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, c
     const unsigned g = (unsigned)nb, t = kCompWarps * 32;
     const float4* raw4 = (const float4*)raw;
     float4* g4 = (float4*)g_raw;
+#define FN_BWD(NB) do { if (noise) k_composite_bwd_reg<NB, true><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); \
+                        else k_composite_bwd_reg<NB, false><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); } while (0)
     switch ((S + 31) / 32) {
-      case 1: k_composite_bwd_reg<1><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
-      case 2: k_composite_bwd_reg<2><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
-      case 3: case 4: k_composite_bwd_reg<4><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
-      case 5: case 6: k_composite_bwd_reg<6><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
-      default: k_composite_bwd_reg<8><<<g, t, 0, s>>>(raw4, z, dnorm, noise, g_rgb, g_depth, g_acc, g4, R, (int)S, white); break;
+      case 1: FN_BWD(1); break;
+      case 2: FN_BWD(2); break;
+      case 3: case 4: FN_BWD(4); break;
+      case 5: case 6: FN_BWD(6); break;
+      default: FN_BWD(8); break;
     }
     return check_launch("composite_bwd");
   }

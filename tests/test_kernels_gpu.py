@@ -339,3 +339,34 @@ def test_composite_bwd_with_raw_noise(F, cuda_device, R, S, white):
     fwd = F.ops.composite_fwd(raw.to(dev), z.to(dev), dn.to(dev), white_bkgd=white, raw_noise=nz.to(dev))
     ref = O.raw2outputs(raw, z, dn, white, nz)
     assert (fwd["rgb"].cpu() - ref["rgb"]).abs().max() <= 1e-5 and (fwd["weights"].cpu() - ref["weights"]).abs().max() <= 1e-5
+
+
+@pytest.mark.parametrize("Nc,Nf", [(64, 128), (32, 32), (64, 64), (128, 128), (128, 256)])
+@pytest.mark.parametrize("kind", ["random", "linspace_row", "sorted", "peaky", "descending"])
+def test_importance_register_path_bit_exact(F, cuda_device, Nc, Nf, kind):
+    """The register-resident kernels (Nc = 32*2^a, Nf = 32*2^b): bit-exact indices, samples and merged depths for random
+    uniforms, the shared deterministic row (sort skipped), per-ray sorted uniforms, peaky weights (many samples in one
+    bin, duplicates) and descending coarse depths (slow in-kernel path)."""
+    R = 777
+    g = _gen(Nc * 1000 + Nf)
+    if kind == "descending":
+        z = O.stratified(torch.full((R,), 6.0), torch.full((R,), 2.0), torch.linspace(0, 1, Nc), torch.rand(R, Nc, generator=g))
+        w = torch.rand(R, Nc, generator=g)
+    else:
+        z, w = _coarse_case(R, Nc, Nc + Nf, peaky=(kind == "peaky"))
+    if kind == "linspace_row":
+        u_dev = torch.linspace(0, 1, Nf)
+        u = u_dev[None].expand(R, Nf)
+    else:
+        u = torch.rand(R, Nf, generator=g)
+        if kind == "sorted":
+            u = torch.sort(u, -1)[0]
+        if kind == "peaky":
+            u[:, 1::2] = u[:, 0::2]
+        u_dev = u
+    ref = O.sample_pdf(z, w, u)
+    got = F.ops.importance(z.to(cuda_device), w.to(cuda_device), u_dev.contiguous().to(cuda_device))
+    assert torch.equal(got["inds"].cpu().long(), ref["inds"])
+    assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
+    assert torch.equal(got["z_f"].cpu(), ref["z_f"])
+    assert torch.allclose(got["z_std"].cpu(), ref["z_std"], rtol=1e-4, atol=1e-6)
