@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libfnerf.so")
-SOURCES = ["api.cu", "sampling.cu", "composite.cu", "pack.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_bwd.cu", "mlp_bwd_tc.cu", "mlp_dgrad_tc.cu"]
+SOURCES = ["api.cu", "sampling.cu", "composite.cu", "pack.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_bwd.cu", "mlp_bwd_tc.cu", "mlp_dgrad_tc.cu", "mlp_bwd_pipe.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -1,0 +1,626 @@
+// Layer-pipelined tensor-core backward of the NeRF MLP (A.4 backward: dgrad + wgrad in ONE kernel) for sm_100a.
+//
+// Why: the tile-major backward (mlp_dgrad_tc.cu + mlp_bwd_tc.cu) writes every gradient image dZ_l to an HBM tape and
+// reads it back for the weight gradients (5 GB + 12 GB per 4096-ray step) and re-streams all transposed weights for
+// every 128-sample tile.  Here every CTA is pinned to ONE layer (one 128-column half of it) for the whole launch:
+//   * its transposed weights W_l^T[half] (64 KB) are loaded ONCE and stay in shared memory;
+//   * its weight-gradient accumulator dW_l[:, half] (256 x 128 fp32) stays in TMEM for the whole launch and is flushed
+//     once with red.global.add;
+//   * per 128-sample tile it loads the incoming gradient tile dZ_l (4 K-block images, written by the CTAs of layer
+//     l+1) and its half of the forward activation H_{l-1} from the tape, runs
+//         dgrad:  dZ_{l-1}[:, half] = (dZ_l . W_l[:, half]) (.) [H_{l-1} > 0]     M = 128 samples, N = 128, K = 256
+//         wgrad:  dW_l[:, half]    += dZ_l^T . H_{l-1}[:, half]                  M = 2 x 128 outputs, N = 128, K = 128 samples
+//     on the SAME shared-memory images (K-major for dgrad, MN-major for wgrad), and hands dZ_{l-1}[:, half] to the CTAs
+//     of layer l-1 through a small ring in global memory that lives in L2 (4 tiles x 64 KB per hand-off).
+// dZ never reaches HBM; the only HBM streams are the forward tape (read once) and g_raw.
+//
+// Grid: kPipeRoles role-halves x kPipeLanes lanes.  Lane g owns the tiles t = g (mod kPipeLanes); the CTAs (role, g) of
+// one lane form a linear pipeline  V -> F -> L7 -> ... -> L1 -> L0  (backward order), each boundary a ring with
+// release/acquire counters in global memory (`ready`: images written, `done`: consumer halves that have the tile in
+// shared memory).  All CTAs must be co-resident (cooperative launch, grid <= #SMs, 1 CTA / SM).
+//   V0, V1   view branch: dZv = (g_rgb . W_rgb) (.) [HV > 0] on CUDA cores, dFEAT[:, half] = dZv . Wv[:, half],
+//            dWv[:, half] += dZv^T . FEAT[:, half];  V1 also dWv[:, 256:283] (direction encoding);  V0 the rgb head;
+//            both the alpha head for their half of H7 (B operand = a bf16 image of g_raw built in shared memory)
+//   F0, F1   feature layer: dZ7[:, half] = (dFEAT . Wf[:, half] + g_sigma (x) w_alpha[half]) (.) [H7 > 0]
+//   Ll_0/1   trunk layers l = 7..1 (layer 5: the trunk block of W5; L5_0 also dW5[:, 0:63] against the xyz encoding)
+//   L0       dW0 += dZ0^T . PE   (no dgrad)
+// Warps (448 threads): 0 loader (bulk TMA + ring flags), 1 MMA issuer, 2..9 epilogue (TMEM -> mask -> bf16 -> staging ->
+// bulk store into the ring), 10..13 bias sums (column sums of the incoming gradient images, in registers).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace fnerf {
+using namespace ptx;
+
+constexpr int kPipeLanes = 7;
+constexpr int kPipeRoles = 19;                 // V0 V1 F0 F1 L7_0 L7_1 ... L1_0 L1_1 L0
+constexpr int kPipeRings = 9;                  // V->F, F->L7, L7->L6, ..., L1->L0
+constexpr int kPipeDepth = 4;                  // tiles per ring
+constexpr int kPipeThreads = 448;
+constexpr uint32_t kImg = 16384, kPairB = 32768, kTileB = 65536;
+constexpr int kMaxPairs = 4;
+// shared memory (role dependent, see the map in the kernel):
+//   trunk: W^T half 64 KB | staging 32 KB | 4 pair slots 128 KB            view: W^T half 32 KB | staging 32 KB | dZv pair 32 KB |
+//   L0:    4 pair slots                                                           G image 16 KB | 3 pair slots 96 KB
+constexpr uint32_t kPOffWt = 0;
+constexpr uint32_t kPOffBar = 229376;
+constexpr uint32_t kPNumBars = 2 * kMaxPairs + 8;
+constexpr uint32_t kPipeSmem = kPOffBar + kPNumBars * 8 + 16 + 1024;
+static_assert(kPipeSmem <= 227 * 1024, "shared memory budget");
+
+enum { ROLE_V = 0, ROLE_T = 1, ROLE_Z = 2 };
+
+struct PipeProduct {            // one weight-gradient product accumulated in TMEM and flushed at the end
+  float* dw;                    // element (lane n of M-block mb, column c) -> dw[(mb*128 + n) * ld_n + (c - k0) * ld_k]
+  int64_t ld_n, ld_k;
+  int tmem_col, n_mb, ncols, k0, n_valid;
+};
+struct PipeRole {
+  int kind, half;
+  int in_ring, out_ring;        // -1: none
+  int wt_chunk0, wt_nchunks;    // section E chunks of W^T (rows [128*half, +128) of each)
+  int x_slot;                   // forward-tape slot of the activation pair (X operand of the main wgrad product)
+  int mask_unit0;               // first ReLU-mask unit of the output columns (-1: none, dFEAT)
+  int rank1;                    // F: add g_sigma (x) w_alpha[half] before the mask
+  int e_slot;                   // forward-tape slot of an extra single image (PE / PED), -1 none
+  int p_slot[2];                // forward-tape slots of extra pairs (HV, H7 half), -1 none
+  float* bias;                  // column sums of the incoming gradient images {2*half, 2*half+1} (Z: all four)
+  PipeProduct prod[3];
+  int nprod;
+};
+struct PipeParams {
+  PipeRole roles[kPipeRoles];
+  const uint8_t* packed; int cond;
+  const float4* g_raw;
+  const uint8_t* fwd_tape; const uint32_t* mask_tape;
+  uint8_t* ring;                // [kPipeRings][kPipeLanes][kPipeDepth] tiles of 64 KB
+  uint32_t* flags;              // ready[kPipeRings][kPipeLanes] then done[...], 32 words apart
+  float* flat_grad;
+  int64_t M, ntiles;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// bounded spin on a monotone counter written by another CTA of this launch; a peer that never arrives (a bug, or CTAs that
+// are not co-resident) aborts the launch after 4 s instead of hanging the GPU
+__device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t target) {
+  if ((int32_t)(ld_acquire_gpu(p) - target) >= 0) return;
+  const uint64_t t0 = global_timer_ns();
+  while ((int32_t)(ld_acquire_gpu(p) - target) < 0) {
+    __nanosleep(64);
+    if (global_timer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__host__ __device__ constexpr uint32_t pipe_idesc_mn(int M, int N) {   // A and B MN-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_constant__ PipeParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int role_id = (int)blockIdx.x / kPipeLanes, lane_g = (int)blockIdx.x % kPipeLanes;
+  const PipeRole& Rl = P.roles[role_id];
+  const int kind = Rl.kind, half = Rl.half;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_my = P.ntiles > lane_g ? (P.ntiles - lane_g + kPipeLanes - 1) / kPipeLanes : 0;   // tiles of this lane
+
+  // ---- shared-memory map --------------------------------------------------------------------------
+  const uint32_t wt_bytes = (uint32_t)Rl.wt_nchunks * kImg;                       // 64 KB (trunk), 32 KB (view), 0 (L0)
+  const uint32_t off_stage = kind == ROLE_Z ? 0u : wt_bytes;
+  const uint32_t off_zv = off_stage + kPairB;                                     // V only: dZv pair, then the G image
+  const uint32_t off_g = off_zv + kPairB;
+  const uint32_t off_ring = kind == ROLE_V ? off_g + kImg : (kind == ROLE_Z ? 0u : off_stage + kPairB);
+  const int npairs = kind == ROLE_V ? 3 : 4;
+  const uint32_t bar0 = base + kPOffBar;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kMaxPairs + s); };
+  const uint32_t bar_dg_full = bar0 + 8u * (2 * kMaxPairs), bar_dg_empty = bar_dg_full + 8u;
+  const uint32_t bar_zv_full = bar_dg_full + 16u, bar_zv_empty = bar_dg_full + 24u;
+  const uint32_t bar_g_full = bar_dg_full + 32u, bar_g_empty = bar_dg_full + 40u;
+  const uint32_t bar_done = bar_dg_full + 48u, bar_wt = bar_dg_full + 56u;
+  const uint32_t tmem_slot = bar0 + 8u * kPNumBars;
+  auto pair_addr = [&](int s) { return base + off_ring + (uint32_t)s * kPairB; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxPairs; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1 + 4); }   // MMA commit + 4 bias warps
+    mbar_init(bar_dg_full, 1);  mbar_init(bar_dg_empty, 8);
+    mbar_init(bar_zv_full, 8);  mbar_init(bar_zv_empty, 1 + 4);
+    mbar_init(bar_g_full, 4);   mbar_init(bar_g_empty, 1);
+    mbar_init(bar_done, 1);     mbar_init(bar_wt, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + kPOffBar + 8 * kPNumBars);
+
+  uint32_t* ready = P.flags;
+  uint32_t* done = P.flags + kPipeRings * kPipeLanes * 32;
+  auto flag_idx = [&](int ring) { return (ring * kPipeLanes + lane_g) * 32; };
+  auto ring_tile = [&](int ring, int64_t i) {
+    return P.ring + ((size_t)(ring * kPipeLanes + lane_g) * kPipeDepth + (size_t)(i % kPipeDepth)) * kTileB;
+  };
+  const int64_t fstride = (int64_t)kTapeFwdSlots * kImg;
+  // pairs a tile consumes, in this order (loader, MMA warp and bias warps walk the same sequence):
+  //   T: A (dZ images 0,1)  B (dZ images 2,3)  C (X pair)  [E (xyz encoding image)]
+  //   V: C (FEAT half pair)  P0  P1  (extra pairs / single image)
+  //   Z: A  B  E
+  const int n_seq = kind == ROLE_T ? (Rl.e_slot >= 0 ? 4 : 3) : 3;
+
+  if (warp == 0) {
+    // ================================ loader ========================================================
+    if (lane == 0 && n_my > 0) {
+      if (wt_bytes) {                                   // stationary W^T half: rows [128*half, +128) of every chunk
+        mbar_expect_tx(bar_wt, wt_bytes);
+        const uint8_t* wsrc = P.packed + sec_e_offset(P.cond);
+        for (int c = 0; c < Rl.wt_nchunks; ++c)
+          bulk_g2s(base + kPOffWt + (uint32_t)c * kImg, wsrc + (size_t)(Rl.wt_chunk0 + c) * kChunkTBytes + (size_t)half * kImg, kImg, bar_wt);
+      }
+      uint32_t pc = 0;
+      auto load = [&](const void* src, uint32_t bytes) {
+        const uint32_t s = pc % npairs;
+        mbar_wait(bar_empty(s), ((pc / npairs) & 1u) ^ 1u);
+        mbar_expect_tx(bar_full(s), bytes);
+        bulk_g2s(pair_addr(s), src, bytes, bar_full(s));
+        ++pc;
+      };
+      for (int64_t i = 0; i < n_my; ++i) {
+        const int64_t tile = lane_g + i * kPipeLanes;
+        const uint8_t* ft = P.fwd_tape + tile * fstride;
+        if (kind != ROLE_V) {
+          // both halves of the producing layer have published their two images of tile i
+          spin_until_ge(ready + flag_idx(Rl.in_ring), (uint32_t)(2 * (i + 1)));
+          spin_until_ge(ready + flag_idx(Rl.in_ring) + 1, (uint32_t)(2 * (i + 1)));
+          fence_proxy_async_global();
+          const uint8_t* src = ring_tile(Rl.in_ring, i);
+          load(src, kPairB);
+          load(src + kPairB, kPairB);
+        }
+        if (kind == ROLE_T) {
+          load(ft + (size_t)Rl.x_slot * kImg, kPairB);
+          if (Rl.e_slot >= 0) load(ft + (size_t)Rl.e_slot * kImg, kImg);
+        } else if (kind == ROLE_Z) {
+          load(ft + (size_t)Rl.e_slot * kImg, kImg);
+        } else {
+          load(ft + (size_t)Rl.x_slot * kImg, kPairB);
+          if (Rl.p_slot[0] >= 0) load(ft + (size_t)Rl.p_slot[0] * kImg, kPairB);
+          else load(ft + (size_t)Rl.e_slot * kImg, kImg);
+          load(ft + (size_t)Rl.p_slot[1] * kImg, kPairB);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ====================================================
+    if (n_my > 0) {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint32_t idesc_dg = umma_idesc_bf16(128, 128);
+      uint32_t pc = 0;
+      auto use = [&](uint32_t& s) {                      // next pair of the sequence: wait until it has landed
+        s = pc % npairs;
+        mbar_wait(bar_full(s), (pc / npairs) & 1u);
+        ++pc;
+      };
+      auto kdesc = [&](uint32_t addr) { return umma_desc_sw128(addr); };
+      auto mndesc = [&](uint32_t addr) { return umma_desc_mn_sw128(addr, kImg); };
+      if (wt_bytes) mbar_wait(bar_wt, 0);
+      for (int64_t i = 0; i < n_my; ++i) {
+        const uint32_t first = i == 0 ? 0u : 1u;         // accumulate flag of the launch-long wgrad accumulators
+        uint32_t sA = 0, sB = 0, sC = 0, sE = 0, sP0 = 0, sP1 = 0;
+        if (kind != ROLE_V) {
+          use(sA); use(sB);
+          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + half, 1u);    // this half holds tile i in shared memory
+        }
+        if (kind == ROLE_T || kind == ROLE_V) {
+          // ---- dgrad: D[128 samples x 128] = A[128 x K] . W^T[half]^T --------------------------------
+          mbar_wait(bar_dg_empty, (uint32_t)(i & 1) ^ 1u);
+          if (kind == ROLE_V) mbar_wait(bar_zv_full, (uint32_t)(i & 1));
+          tc_fence_after();
+          if (elect_one()) {
+            const int nkb = kind == ROLE_V ? 2 : 4;
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint32_t img = kind == ROLE_V ? base + off_zv + (uint32_t)kb * kImg
+                                                  : pair_addr(kb < 2 ? sA : sB) + (uint32_t)(kb & 1) * kImg;
+              const uint64_t a = kdesc(img), b = kdesc(base + kPOffWt + (uint32_t)kb * kImg);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(tm, a + (uint64_t)(2 * ks), b + (uint64_t)(2 * ks), idesc_dg, (kb | ks) ? 1u : 0u);
+            }
+            umma_commit(bar_dg_full);
+          }
+          __syncwarp();
+        }
+        // ---- main wgrad product ----------------------------------------------------------------------
+        if (kind == ROLE_Z) use(sE); else use(sC);
+        tc_fence_after();
+        if (elect_one()) {
+          const PipeProduct& pr = Rl.prod[0];
+          const uint32_t idesc = pipe_idesc_mn(128, pr.ncols);
+          const uint64_t b0 = mndesc(pair_addr(kind == ROLE_Z ? sE : sC));
+          for (int mb = 0; mb < pr.n_mb; ++mb) {
+            const uint64_t a0 = mndesc(kind == ROLE_V ? base + off_zv : pair_addr(mb ? sB : sA));
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16(tm + (uint32_t)(pr.tmem_col + mb * pr.ncols), a0 + (uint64_t)(ks * 128), b0 + (uint64_t)(ks * 128), idesc,
+                        (ks == 0) ? first : 1u);
+          }
+        }
+        __syncwarp();
+        // ---- extra products ----------------------------------------------------------------------------
+        if (kind == ROLE_T && Rl.e_slot >= 0) {            // L5_0: dW5[:, 0:63] += dZ5^T . PE
+          use(sE);
+          tc_fence_after();
+          if (elect_one()) {
+            const PipeProduct& pr = Rl.prod[1];
+            const uint32_t idesc = pipe_idesc_mn(128, pr.ncols);
+            const uint64_t b0 = mndesc(pair_addr(sE));
+            for (int mb = 0; mb < 2; ++mb) {
+              const uint64_t a0 = mndesc(pair_addr(mb ? sB : sA));
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                umma_bf16(tm + (uint32_t)(pr.tmem_col + mb * pr.ncols), a0 + (uint64_t)(ks * 128), b0 + (uint64_t)(ks * 128), idesc,
+                          (ks == 0) ? first : 1u);
+            }
+          }
+          __syncwarp();
+        }
+        if (kind == ROLE_V) {
+          use(sP0); use(sP1);
+          mbar_wait(bar_g_full, (uint32_t)(i & 1));
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t g0 = mndesc(base + off_g);
+            {   // prod[1]: V0: rgb head, A = HV pair, B = G image;  V1: dWv[:, 256:283], A = dZv, B = PED image
+              const PipeProduct& pr = Rl.prod[1];
+              const uint32_t idesc = pipe_idesc_mn(128, pr.ncols);
+              const uint64_t a0 = mndesc(Rl.p_slot[0] >= 0 ? pair_addr(sP0) : base + off_zv);
+              const uint64_t b0 = Rl.p_slot[0] >= 0 ? g0 : mndesc(pair_addr(sP0));
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                umma_bf16(tm + (uint32_t)pr.tmem_col, a0 + (uint64_t)(ks * 128), b0 + (uint64_t)(ks * 128), idesc, (ks == 0) ? first : 1u);
+            }
+            {   // prod[2]: alpha head for this half of H7: A = H7 pair, B = G image
+              const PipeProduct& pr = Rl.prod[2];
+              const uint32_t idesc = pipe_idesc_mn(128, pr.ncols);
+              const uint64_t a0 = mndesc(pair_addr(sP1));
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                umma_bf16(tm + (uint32_t)pr.tmem_col, a0 + (uint64_t)(ks * 128), g0 + (uint64_t)(ks * 128), idesc, (ks == 0) ? first : 1u);
+            }
+          }
+          __syncwarp();
+        }
+        // ---- release everything this tile read ---------------------------------------------------------
+        if (elect_one()) {
+          if (kind != ROLE_V) { umma_commit(bar_empty(sA)); umma_commit(bar_empty(sB)); }
+          if (kind == ROLE_Z) umma_commit(bar_empty(sE)); else umma_commit(bar_empty(sC));
+          if (kind == ROLE_T && Rl.e_slot >= 0) umma_commit(bar_empty(sE));
+          if (kind == ROLE_V) {
+            umma_commit(bar_empty(sP0)); umma_commit(bar_empty(sP1));
+            umma_commit(bar_zv_empty); umma_commit(bar_g_empty);
+          }
+          if (i == n_my - 1) umma_commit(bar_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 10) {
+    // ================================ epilogue warps ================================================
+    const uint32_t q = (uint32_t)warp & 3u;                   // TMEM lane quadrant of this warp
+    const uint32_t j = (uint32_t)(warp - 2) >> 2;             // output image of the half (64 columns)
+    const uint32_t row = q * 32u + (uint32_t)lane;
+    const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
+    const float* aux = reinterpret_cast<const float*>(P.packed + kSecBOffset);
+    float gs0 = 0.f, gs1 = 0.f, gs2 = 0.f, gs3 = 0.f;         // V0: sums of g_raw (head bias gradients)
+    if (kind != ROLE_Z) {
+      const uint32_t stage_row = base + off_stage + j * kImg + row * 128u;
+      for (int64_t i = 0; i < n_my; ++i) {
+        const int64_t tile = lane_g + i * kPipeLanes;
+        const int64_t g = tile * 128 + row;
+        const uint32_t* mtile = P.mask_tape + (size_t)tile * (kMaskUnits * 128) + row;
+        float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((kind == ROLE_V || Rl.rank1) && g < P.M) gr = __ldg(P.g_raw + g);
+        if (kind == ROLE_V) {
+          // ---- dZv image j = (g_rgb . W_rgb) (.) [HV > 0], columns [64 j, 64 j + 64) -------------------
+          const float* wrgb = aux + kAuxWRgb;
+          mbar_wait(bar_zv_empty, (uint32_t)(i & 1) ^ 1u);
+          const uint32_t zv_row = base + off_zv + j * kImg + row * 128u;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t mb = __ldg(mtile + (kMaskUnitHv + (int)j * 2 + u) * 128);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int ii = c * 4 + jj, col = (int)j * 64 + u * 32 + 2 * ii;
+                float lo = gr.x * __ldg(wrgb + col) + gr.y * __ldg(wrgb + kWV + col) + gr.z * __ldg(wrgb + 2 * kWV + col);
+                float hi = gr.x * __ldg(wrgb + col + 1) + gr.y * __ldg(wrgb + kWV + col + 1) + gr.z * __ldg(wrgb + 2 * kWV + col + 1);
+                if (!(mb & (1u << ii))) lo = 0.0f;
+                if (!(mb & (1u << (16 + ii)))) hi = 0.0f;
+                pk[jj] = pack_bf16(lo, hi);
+              }
+              const uint32_t c16 = (uint32_t)(u * 4 + c);
+              st_shared_v4(zv_row + ((c16 ^ (row & 7u)) << 4), pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_zv_full);
+          if (j == 0) {                                       // the bf16 image of g_raw the head products multiply with
+            mbar_wait(bar_g_empty, (uint32_t)(i & 1) ^ 1u);
+            // logical 16-byte chunks 0 and 1 of the row (N = 16 columns are multiplied): (g_r, g_g, g_b, g_sigma, 0 ...)
+            st_shared_v4(base + off_g + row * 128u + ((row & 7u) << 4), pack_bf16(gr.x, gr.y), pack_bf16(gr.z, gr.w), 0u, 0u);
+            st_shared_v4(base + off_g + row * 128u + (((row & 7u) ^ 1u) << 4), 0u, 0u, 0u, 0u);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_g_full);
+            if (half == 0) { gs0 += gr.x; gs1 += gr.y; gs2 += gr.z; gs3 += gr.w; }
+          }
+        }
+        // ---- dgrad epilogue: accumulator -> (+ rank-1 sigma term) -> ReLU mask -> bf16 -> staging image j -----
+        uint32_t mk[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (Rl.mask_unit0 >= 0) {
+          mk[0] = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2) * 128);
+          mk[1] = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2 + 1) * 128);
+        }
+        mbar_wait(bar_dg_full, (uint32_t)(i & 1));
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem_row + j * 64u, v0);
+        tmem_ld32(tmem_row + j * 64u + 32u, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dg_empty);               // the accumulator may be overwritten by the next tile
+        group_bar(2u + j, 128u);                                // the previous store of this staging image has read it
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t* v = u ? v1 : v0;
+          const int col0 = half * 128 + (int)j * 64 + u * 32;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int ii = c * 4 + jj;
+              float lo = __uint_as_float(v[2 * ii]), hi = __uint_as_float(v[2 * ii + 1]);
+              if (Rl.rank1) {
+                lo = fmaf(gr.w, __ldg(aux + kAuxWAlpha + col0 + 2 * ii), lo);
+                hi = fmaf(gr.w, __ldg(aux + kAuxWAlpha + col0 + 2 * ii + 1), hi);
+              }
+              if (!(mk[u] & (1u << ii))) lo = 0.0f;
+              if (!(mk[u] & (1u << (16 + ii)))) hi = 0.0f;
+              pk[jj] = pack_bf16(lo, hi);
+            }
+            const uint32_t c16 = (uint32_t)(u * 4 + c);
+            st_shared_v4(stage_row + ((c16 ^ (row & 7u)) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        group_bar(4u + j, 128u);                                // image j of this tile is complete in shared memory
+        if (q == 0 && lane == 0) {
+          // hand image 2*half + j of tile i to the next layer: ring slot free? -> bulk store -> publish
+          if (i >= kPipeDepth) {                              // every consumer half has tile i - depth in its shared memory
+            spin_until_ge(done + flag_idx(Rl.out_ring), (uint32_t)(i - kPipeDepth + 1));
+            if (Rl.out_ring != kPipeRings - 1) spin_until_ge(done + flag_idx(Rl.out_ring) + 1, (uint32_t)(i - kPipeDepth + 1));
+          }
+          bulk_s2g(ring_tile(Rl.out_ring, i) + (size_t)(2 * half + (int)j) * kImg, base + off_stage + j * kImg, kImg);
+          bulk_commit();
+          bulk_wait_all<0>();
+          fence_proxy_async_global();
+          __threadfence();
+          red_release_gpu_add(ready + flag_idx(Rl.out_ring) + half, 1u);
+        }
+      }
+    }
+    // ---- flush the launch-long weight-gradient accumulators -------------------------------------------
+    if (n_my > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      for (int p = 0; p < Rl.nprod; ++p) {
+        const PipeProduct& pr = Rl.prod[p];
+        const bool vec = pr.ld_k == 1 && pr.k0 == 0 && (pr.ld_n & 3) == 0 && (pr.n_valid & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(pr.dw) & 15u) == 0;
+        for (int mb = 0; mb < pr.n_mb; ++mb) {
+          float* out = pr.dw + (int64_t)(mb * 128 + (int)row) * pr.ld_n;
+          // the two warps of a lane quadrant split the 32-column groups
+          for (int c0 = (int)j * 32; c0 < pr.ncols && c0 < pr.n_valid; c0 += 64) {
+            uint32_t v[32];
+            tmem_ld32(tmem_row + (uint32_t)(pr.tmem_col + mb * pr.ncols + c0), v);
+            tmem_ld_wait();
+            if (vec) {
+#pragma unroll
+              for (int c = 0; c < 32; c += 4)
+                if (c0 + c < pr.n_valid)
+                  red_add_v4(out + c0 + c, __uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (c0 + c >= pr.k0 && c0 + c < pr.n_valid) atomicAdd(out + (int64_t)(c0 + c - pr.k0) * pr.ld_k, __uint_as_float(v[c]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      if (kind == ROLE_V && half == 0 && j == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gs1 += __shfl_xor_sync(0xffffffffu, gs1, o);
+          gs2 += __shfl_xor_sync(0xffffffffu, gs2, o); gs3 += __shfl_xor_sync(0xffffffffu, gs3, o);
+        }
+        if (lane == 0) {
+          atomicAdd(P.flat_grad + flat_bias_offset(11, P.cond), gs0);
+          atomicAdd(P.flat_grad + flat_bias_offset(11, P.cond) + 1, gs1);
+          atomicAdd(P.flat_grad + flat_bias_offset(11, P.cond) + 2, gs2);
+          atomicAdd(P.flat_grad + flat_bias_offset(8, P.cond), gs3);
+        }
+      }
+    }
+  } else {
+    // ================================ bias warps ====================================================
+    // column sums of the incoming gradient images (bias gradients), accumulated in registers over the launch: thread e
+    // owns the column pair (2p, 2p+1) of image `im` over the rows [64 rh, 64 rh + 64)
+    const int e = (int)threadIdx.x - 320;                 // 0..127
+    const uint32_t p = (uint32_t)e & 31u;
+    const int sel = e >> 5;                               // warp of the four
+    float b0 = 0.0f, b1 = 0.0f, c0 = 0.0f, c1 = 0.0f;
+    auto colsum = [&](const uint8_t* img, uint32_t r0, uint32_t nrows, float& s0, float& s1) {
+      const uint8_t* src = img + (p & 3u) * 4u;
+#pragma unroll 8
+      for (uint32_t r = r0; r < r0 + nrows; ++r) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(src + r * 128u + (((p >> 2) ^ (r & 7u)) << 4));
+        s0 += __uint_as_float(w << 16);
+        s1 += __uint_as_float(w & 0xFFFF0000u);
+      }
+    };
+    uint32_t pc = 0;
+    for (int64_t i = 0; i < n_my; ++i) {
+      for (int k = 0; k < n_seq; ++k, ++pc) {
+        const uint32_t s = pc % npairs;
+        mbar_wait(bar_full(s), (pc / npairs) & 1u);
+        const uint8_t* pair = base_ptr + off_ring + s * kPairB;
+        if (kind == ROLE_T && k == half) {
+          // images {2 half, 2 half + 1} of dZ: warp sel -> image sel / 2, rows half sel % 2
+          colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, b0, b1);
+        } else if (kind == ROLE_Z && k < 2) {
+          // all four images: pair k, warp sel -> image sel / 2 of the pair, rows half sel % 2
+          if (k == 0) colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, b0, b1);
+          else colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, c0, c1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty(s));
+      }
+      if (kind == ROLE_V) {
+        mbar_wait(bar_zv_full, (uint32_t)(i & 1));
+        // dZv image `half`: 64 columns = 32 pairs; warp sel sums rows [32 sel, +32)
+        colsum(base_ptr + off_zv + (uint32_t)half * kImg, (uint32_t)sel * 32u, 32u, b0, b1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_zv_empty);
+      }
+    }
+    if (n_my > 0 && Rl.bias != nullptr) {
+      if (kind == ROLE_T) {
+        float* dst = Rl.bias + half * 128 + (sel >> 1) * 64 + 2 * (int)p;
+        atomicAdd(dst, b0); atomicAdd(dst + 1, b1);
+      } else if (kind == ROLE_Z) {
+        float* dst = Rl.bias + (sel >> 1) * 64 + 2 * (int)p;
+        atomicAdd(dst, b0); atomicAdd(dst + 1, b1);
+        atomicAdd(dst + 128, c0); atomicAdd(dst + 129, c1);
+      } else {
+        float* dst = Rl.bias + half * 64 + 2 * (int)p;
+        atomicAdd(dst, b0); atomicAdd(dst + 1, b1);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int64_t mlp_bwd_pipe_workspace_bytes() {
+  return (int64_t)kPipeRings * kPipeLanes * kPipeDepth * kTileB + 2 * (int64_t)kPipeRings * kPipeLanes * 32 * 4 + 1024;
+}
+
+// flat_grad += dL/dparams of an UNCONDITIONED network from its forward tape and g_raw[M,4]
+int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape, float* flat_grad, void* ws, int64_t M, cudaStream_t s) {
+  if (M == 0) return 0;
+  const int cond = 0;
+  const int64_t ntiles = (M + 127) / 128;
+  static DeviceOnce once;
+  if (cudaError_t e = opt_in_smem_once(once, k_mlp_bwd_pipe, kPipeSmem)) return set_error((int)e, "mlp_bwd_pipe attr: %s", cudaGetErrorString(e));
+  if (num_sms() < kPipeRoles * kPipeLanes) return set_error(FNERF_ERR_ARG, "mlp_bwd_pipe: needs %d co-resident CTAs", kPipeRoles * kPipeLanes);
+  PipeParams P = {};
+  P.packed = reinterpret_cast<const uint8_t*>(packed); P.cond = cond;
+  P.g_raw = reinterpret_cast<const float4*>(g_raw);
+  P.fwd_tape = reinterpret_cast<const uint8_t*>(tape);
+  P.mask_tape = reinterpret_cast<const uint32_t*>(P.fwd_tape + ntiles * (int64_t)kTapeFwdSlots * kImg);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  P.ring = w8;
+  P.flags = reinterpret_cast<uint32_t*>(w8 + (int64_t)kPipeRings * kPipeLanes * kPipeDepth * kTileB);
+  P.flat_grad = flat_grad; P.M = M; P.ntiles = ntiles;
+  auto gw = [&](int l) { return flat_grad + flat_weight_offset(l, cond); };
+  auto gb = [&](int l) { return flat_grad + flat_bias_offset(l, cond); };
+  const int in5 = kPE + kW;
+  int r = 0;
+  auto prod = [](float* dw, int64_t ld_n, int64_t ld_k, int tmem_col, int n_mb, int ncols, int k0, int n_valid) {
+    PipeProduct p; p.dw = dw; p.ld_n = ld_n; p.ld_k = ld_k; p.tmem_col = tmem_col; p.n_mb = n_mb; p.ncols = ncols; p.k0 = k0; p.n_valid = n_valid;
+    return p;
+  };
+  // V0 / V1
+  for (int h = 0; h < 2; ++h) {
+    PipeRole& R = P.roles[r++];
+    R.kind = ROLE_V; R.half = h; R.in_ring = -1; R.out_ring = 0; R.wt_chunk0 = 0; R.wt_nchunks = 2;
+    R.x_slot = kTapeSlotFeat + 2 * h; R.mask_unit0 = -1; R.rank1 = 0;
+    R.bias = gb(10);
+    R.prod[0] = prod(gw(10) + 128 * h, kW + kPED, 1, 128, 1, 128, 0, 128);
+    if (h == 0) {
+      R.e_slot = -1; R.p_slot[0] = kTapeSlotHv; R.p_slot[1] = kTapeSlotH + 28;
+      R.prod[1] = prod(gw(11), 1, kWV, 256, 1, 16, 0, 3);                        // rgb_linear.weight[c][n]
+    } else {
+      R.e_slot = kTapeSlotPed; R.p_slot[0] = -1; R.p_slot[1] = kTapeSlotH + 30;
+      R.prod[1] = prod(gw(10) + kW, kW + kPED, 1, 256, 1, 32, 0, kPED);          // views weight, direction columns
+    }
+    R.prod[2] = prod(gw(8) + 128 * h, 1, 0, 288, 1, 16, 3, 4);                    // alpha_linear.weight[128 h + n] (column 3 = sigma)
+    R.nprod = 3;
+  }
+  // F0 / F1, L7 .. L1
+  for (int st = 1; st <= 8; ++st) {
+    const int layer = st == 1 ? 9 : 9 - st;                                      // flat layer id: 9 = feature, then 7..1
+    for (int h = 0; h < 2; ++h) {
+      PipeRole& R = P.roles[r++];
+      R.kind = ROLE_T; R.half = h; R.in_ring = st - 1; R.out_ring = st;
+      R.wt_chunk0 = st == 1 ? 2 : 6 + 4 * (st - 2); R.wt_nchunks = 4;
+      const int hsrc = st == 1 ? 7 : layer - 1;                                  // forward activation H_hsrc is the X operand and the mask
+      R.x_slot = kTapeSlotH + 4 * hsrc + 2 * h;
+      R.mask_unit0 = hsrc * 8 + 4 * h;
+      R.rank1 = st == 1;
+      R.e_slot = -1; R.p_slot[0] = R.p_slot[1] = -1;
+      R.bias = gb(layer);
+      const int ld = layer == 5 ? in5 : kW;
+      R.prod[0] = prod(gw(layer) + (layer == 5 ? kPE : 0) + 128 * h, ld, 1, 128, 2, 128, 0, 128);
+      R.nprod = 1;
+      if (layer == 5 && h == 0) {
+        R.e_slot = kTapeSlotPe;
+        R.prod[1] = prod(gw(5), in5, 1, 384, 2, 64, 0, kPE);
+        R.nprod = 2;
+      }
+    }
+  }
+  {
+    PipeRole& R = P.roles[r++];
+    R.kind = ROLE_Z; R.half = 0; R.in_ring = 8; R.out_ring = -1; R.wt_chunk0 = 0; R.wt_nchunks = 0; R.x_slot = 0;
+    R.mask_unit0 = -1; R.rank1 = 0; R.e_slot = kTapeSlotPe; R.p_slot[0] = R.p_slot[1] = -1;
+    R.bias = gb(0);
+    R.prod[0] = prod(gw(0), kPE, 1, 0, 2, 64, 0, kPE);
+    R.nprod = 1;
+  }
+  cudaError_t e = cudaMemsetAsync(P.flags, 0, 2 * (size_t)kPipeRings * kPipeLanes * 32 * 4, s);
+  if (e != cudaSuccess) return set_error((int)e, "mlp_bwd_pipe memset: %s", cudaGetErrorString(e));
+  void* args[] = {(void*)&P};
+  e = cudaLaunchCooperativeKernel((const void*)k_mlp_bwd_pipe, dim3(kPipeRoles * kPipeLanes), dim3(kPipeThreads), args, kPipeSmem, s);
+  if (e != cudaSuccess) return set_error((int)e, "mlp_bwd_pipe launch: %s", cudaGetErrorString(e));
+  return check_launch("mlp_bwd_pipe");
+}
+
+}  // namespace fnerf

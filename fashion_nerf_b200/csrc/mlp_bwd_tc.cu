@@ -13,6 +13,7 @@
 //       tile the CTA owns, then flushed once with fp32 atomicAdd into the flat gradient buffer.
 // One K=16 MMA consumes 16 samples = two 8-row swizzle atoms (SBO = 1024 B); a pipeline stage is half a
 // tile (64 samples = 8 KB of every K-block image, one bulk copy each).
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -226,8 +227,25 @@ int64_t mlp_tape_bytes(int64_t M) {
   const int64_t ntiles = (M + 127) / 128;
   return ntiles * ((int64_t)kTapeFwdSlots * 16384 + kMaskTileBytes);
 }
-// backward tape + (conditioned networks) the per-sample garment codes as 4 K-block images per tile
-int64_t mlp_bwd_from_tape_workspace_bytes(int64_t M) { return (M + 127) / 128 * (int64_t)(kTapeBwdSlots + 4) * 16384; }
+int64_t mlp_bwd_pipe_workspace_bytes();
+int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape, float* flat_grad, void* ws, int64_t M, cudaStream_t s);
+
+// Which backward runs from a forward tape: the layer-pipelined fused dgrad + wgrad kernel (mlp_bwd_pipe.cu) for
+// unconditioned networks; the tile-major dgrad chain + grouped wgrad launch below for conditioned ones (their extra
+// code-block product needs a 256 x 256 accumulator no pipeline role has room for).  FNERF_BWD_PIPE=0 forces the latter.
+static bool use_bwd_pipe(int cond) {
+  static std::once_flag flag;
+  static int enabled = 1;
+  std::call_once(flag, [] { const char* e = getenv("FNERF_BWD_PIPE"); if (e) enabled = atoi(e) != 0; });
+  return enabled && !cond;
+}
+
+// backward tape + (conditioned networks) the per-sample garment codes as 4 K-block images per tile; or the pipeline's
+// hand-off rings
+int64_t mlp_bwd_from_tape_workspace_bytes(int64_t M) {
+  const int64_t tile_major = (M + 127) / 128 * (int64_t)(kTapeBwdSlots + 4) * 16384, pipe = mlp_bwd_pipe_workspace_bytes();
+  return tile_major > pipe ? tile_major : pipe;
+}
 
 // A.8 backward: the code block of W5 sees, for every sample, the code of its ray.  Written once per backward as
 // bf16 K-block images (same layout as the activation tape) so that dW5[:, 63:319] is one more wgrad product.
@@ -273,6 +291,7 @@ int launch_mlp_bwd_from_tape(const void* packed, int cond, const float* g_raw, c
                              const int32_t* cond_index, int64_t C, int64_t S, float* flat_grad, void* ws, int64_t M,
                              cudaStream_t s) {
   if (M == 0) return 0;
+  if (use_bwd_pipe(cond)) return launch_mlp_bwd_pipe(packed, g_raw, tape, flat_grad, ws, M, s);
   const int64_t ntiles = (M + 127) / 128;
   const uint8_t* fwd_tape = reinterpret_cast<const uint8_t*>(tape);
   const uint32_t* mask_tape = reinterpret_cast<const uint32_t*>(fwd_tape + ntiles * (int64_t)kTapeFwdSlots * 16384);
