@@ -81,6 +81,7 @@ SIGNATURES = {
                                     c_int64, c_int64, c_int, c_void_p]),
     "fnerf_render_rays_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "fnerf_render_rays": (c_int, [ctypes.POINTER(RenderArgs), c_void_p]),
+    "fnerf_debug_pipe_stats": (c_int, [c_void_p]),
     "fnerf_debug_wgrad_tc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int, c_int64, c_void_p]),
 }
 

@@ -35,18 +35,20 @@ using namespace ptx;
 constexpr int kPipeLanes = 7;
 constexpr int kPipeRoles = 19;                 // V0 V1 F0 F1 L7_0 L7_1 ... L1_0 L1_1 L0
 constexpr int kPipeRings = 9;                  // V->F, F->L7, L7->L6, ..., L1->L0
-constexpr int kPipeDepth = 4;                  // tiles per ring
-constexpr int kPipeThreads = 448;
+constexpr int kPipeDepth = 8;                  // tiles per ring (covers the store -> flag -> poll -> load round trip)
+constexpr int kPipeThreads = 512;              // warps: 0 loader, 1 MMA, 2..9 epilogue, 10..13 bias sums, 14..15 ring stores
 constexpr uint32_t kImg = 16384, kPairB = 32768, kTileB = 65536;
 constexpr int kMaxPairs = 4;
 // shared memory (role dependent, see the map in the kernel):
-//   trunk: W^T half 64 KB | staging 32 KB | 4 pair slots 128 KB            view: W^T half 32 KB | staging 32 KB | dZv pair 32 KB |
-//   L0:    4 pair slots                                                           G image 16 KB | 3 pair slots 96 KB
+//   trunk: W^T half 64 KB | staging 32 KB | 4 pair slots 128 KB
+//   view:  W^T half 32 KB | staging 32 KB | dZv pair 32 KB | G image 16 KB | W_rgb tile 16 KB | 3 pair slots 96 KB
+//   L0:    4 pair slots
 constexpr uint32_t kPOffWt = 0;
 constexpr uint32_t kPOffBar = 229376;
-constexpr uint32_t kPNumBars = 2 * kMaxPairs + 8;
+constexpr uint32_t kPNumBars = 2 * kMaxPairs + 14;
 constexpr uint32_t kPipeSmem = kPOffBar + kPNumBars * 8 + 16 + 1024;
 static_assert(kPipeSmem <= 227 * 1024, "shared memory budget");
+constexpr int kPipeStatSlots = 8;              // per role: cycles the warps spent waiting (debug, see fnerf_debug_pipe_stats)
 
 enum { ROLE_V = 0, ROLE_T = 1, ROLE_Z = 2 };
 
@@ -74,8 +76,9 @@ struct PipeParams {
   const float4* g_raw;
   const uint8_t* fwd_tape; const uint32_t* mask_tape;
   uint8_t* ring;                // [kPipeRings][kPipeLanes][kPipeDepth] tiles of 64 KB
-  uint32_t* flags;              // ready[kPipeRings][kPipeLanes] then done[...], 32 words apart
+  uint32_t* flags;              // ready[kPipeRings][kPipeLanes][2 halves] then done[...], 32 words per (ring, lane)
   float* flat_grad;
+  unsigned long long* stats;    // nullable: [kPipeRoles][kPipeStatSlots] summed wait cycles
   int64_t M, ntiles;
 };
 
@@ -98,16 +101,20 @@ __device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t target
   if ((int32_t)(ld_acquire_gpu(p) - target) >= 0) return;
   const uint64_t t0 = global_timer_ns();
   while ((int32_t)(ld_acquire_gpu(p) - target) < 0) {
-    __nanosleep(64);
+    __nanosleep(32);
     if (global_timer_ns() - t0 > 4000000000ull) __trap();
   }
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-__device__ __forceinline__ void group_bar(uint32_t id, uint32_t nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __host__ __device__ constexpr uint32_t pipe_idesc_mn(int M, int N) {   // A and B MN-major
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// mbarrier wait that also accounts the cycles spent (debug statistics)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 
 __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_constant__ PipeParams P) {
@@ -123,17 +130,22 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
   // ---- shared-memory map --------------------------------------------------------------------------
   const uint32_t wt_bytes = (uint32_t)Rl.wt_nchunks * kImg;                       // 64 KB (trunk), 32 KB (view), 0 (L0)
   const uint32_t off_stage = kind == ROLE_Z ? 0u : wt_bytes;
-  const uint32_t off_zv = off_stage + kPairB;                                     // V only: dZv pair, then the G image
+  const uint32_t off_zv = off_stage + kPairB;                                     // V only: dZv pair, G image, W_rgb tile
   const uint32_t off_g = off_zv + kPairB;
-  const uint32_t off_ring = kind == ROLE_V ? off_g + kImg : (kind == ROLE_Z ? 0u : off_stage + kPairB);
+  const uint32_t off_wrgb = off_g + kImg;
+  const uint32_t off_ring = kind == ROLE_V ? off_wrgb + kImg : (kind == ROLE_Z ? 0u : off_stage + kPairB);
   const int npairs = kind == ROLE_V ? 3 : 4;
   const uint32_t bar0 = base + kPOffBar;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kMaxPairs + s); };
-  const uint32_t bar_dg_full = bar0 + 8u * (2 * kMaxPairs), bar_dg_empty = bar_dg_full + 8u;
-  const uint32_t bar_zv_full = bar_dg_full + 16u, bar_zv_empty = bar_dg_full + 24u;
-  const uint32_t bar_g_full = bar_dg_full + 32u, bar_g_empty = bar_dg_full + 40u;
-  const uint32_t bar_done = bar_dg_full + 48u, bar_wt = bar_dg_full + 56u;
+  const uint32_t bx = bar0 + 8u * (2 * kMaxPairs);
+  const uint32_t bar_dg_full = bx, bar_dg_empty = bx + 8u;
+  const uint32_t bar_zv_full = bx + 16u, bar_zv_empty = bx + 24u;
+  const uint32_t bar_g_full = bx + 32u, bar_g_empty = bx + 40u;
+  const uint32_t bar_done = bx + 48u, bar_wt = bx + 56u;
+  const uint32_t bar_zacc_full = bx + 64u;
+  auto bar_img_full = [&](uint32_t j) { return bx + 72u + 8u * j; };
+  auto bar_img_empty = [&](uint32_t j) { return bx + 88u + 8u * j; };
   const uint32_t tmem_slot = bar0 + 8u * kPNumBars;
   auto pair_addr = [&](int s) { return base + off_ring + (uint32_t)s * kPairB; };
 
@@ -141,11 +153,33 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     for (int s = 0; s < kMaxPairs; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1 + 4); }   // MMA commit + 4 bias warps
     mbar_init(bar_dg_full, 1);  mbar_init(bar_dg_empty, 8);
     mbar_init(bar_zv_full, 8);  mbar_init(bar_zv_empty, 1 + 4);
-    mbar_init(bar_g_full, 4);   mbar_init(bar_g_empty, 1);
+    mbar_init(bar_g_full, 8);   mbar_init(bar_g_empty, 1);
     mbar_init(bar_done, 1);     mbar_init(bar_wt, 1);
+    mbar_init(bar_zacc_full, 1);
+    for (uint32_t j = 0; j < 2; ++j) { mbar_init(bar_img_full(j), 4); mbar_init(bar_img_empty(j), 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (kind == ROLE_V) {
+    // constant B operand of the dZv product (K-major, K = 16): row n = HV unit n, columns (k): 0..2 = bf16(w_c[n]), 3 = 0
+    // (the sigma column of the G image), 4..6 = bf16(w_c[n]) again (they meet the low parts of g), 7..9 = the low parts
+    // of w_c[n] (they meet the high parts of g): g.w to ~16 mantissa bits with bf16 operands
+    const float* wrgb = reinterpret_cast<const float*>(P.packed + kSecBOffset) + kAuxWRgb;
+    for (int n = threadIdx.x; n < kWV; n += kPipeThreads) {
+      float w[3];
+      uint32_t hi[3], lo[3];
+      for (int c = 0; c < 3; ++c) {
+        w[c] = wrgb[c * kWV + n];
+        hi[c] = pack_bf16(w[c], 0.0f) & 0xFFFFu;
+        lo[c] = pack_bf16(w[c] - __uint_as_float(hi[c] << 16), 0.0f) & 0xFFFFu;
+      }
+      const uint32_t r = (uint32_t)n;
+      // chunk 0: k = 0..7 = (h0, h1, h2, 0, h0, h1, h2, l0)   chunk 1: k = 8..15 = (l1, l2, 0, ...)
+      st_shared_v4(base + off_wrgb + r * 128u + ((r & 7u) << 4), hi[0] | (hi[1] << 16), hi[2], hi[0] | (hi[1] << 16), hi[2] | (lo[0] << 16));
+      st_shared_v4(base + off_wrgb + r * 128u + (((r & 7u) ^ 1u) << 4), lo[1] | (lo[2] << 16), 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -158,11 +192,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     return P.ring + ((size_t)(ring * kPipeLanes + lane_g) * kPipeDepth + (size_t)(i % kPipeDepth)) * kTileB;
   };
   const int64_t fstride = (int64_t)kTapeFwdSlots * kImg;
-  // pairs a tile consumes, in this order (loader, MMA warp and bias warps walk the same sequence):
-  //   T: A (dZ images 0,1)  B (dZ images 2,3)  C (X pair)  [E (xyz encoding image)]
-  //   V: C (FEAT half pair)  P0  P1  (extra pairs / single image)
+  // pairs a tile consumes, in this order (loader, MMA warp and bias warps walk the same sequence of slots):
+  //   T: A (dZ images 0,1)  C (X pair)  B (dZ images 2,3)  [E (xyz encoding image)]
+  //   V: C (FEAT half pair)  P0 (HV pair | PED image)  P1 (H7 half pair)
   //   Z: A  B  E
   const int n_seq = kind == ROLE_T ? (Rl.e_slot >= 0 ? 4 : 3) : 3;
+  long long w0 = 0, w1 = 0, w2 = 0;            // debug statistics: cycles spent waiting
 
   if (warp == 0) {
     // ================================ loader ========================================================
@@ -176,7 +211,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
       uint32_t pc = 0;
       auto load = [&](const void* src, uint32_t bytes) {
         const uint32_t s = pc % npairs;
-        mbar_wait(bar_empty(s), ((pc / npairs) & 1u) ^ 1u);
+        mbar_wait_t(bar_empty(s), ((pc / npairs) & 1u) ^ 1u, w1);
         mbar_expect_tx(bar_full(s), bytes);
         bulk_g2s(pair_addr(s), src, bytes, bar_full(s));
         ++pc;
@@ -184,19 +219,24 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
       for (int64_t i = 0; i < n_my; ++i) {
         const int64_t tile = lane_g + i * kPipeLanes;
         const uint8_t* ft = P.fwd_tape + tile * fstride;
+        const uint8_t* src = nullptr;
         if (kind != ROLE_V) {
           // both halves of the producing layer have published their two images of tile i
+          const long long t0 = clock64();
           spin_until_ge(ready + flag_idx(Rl.in_ring), (uint32_t)(2 * (i + 1)));
           spin_until_ge(ready + flag_idx(Rl.in_ring) + 1, (uint32_t)(2 * (i + 1)));
+          w0 += clock64() - t0;
           fence_proxy_async_global();
-          const uint8_t* src = ring_tile(Rl.in_ring, i);
-          load(src, kPairB);
-          load(src + kPairB, kPairB);
+          src = ring_tile(Rl.in_ring, i);
         }
         if (kind == ROLE_T) {
+          load(src, kPairB);
           load(ft + (size_t)Rl.x_slot * kImg, kPairB);
+          load(src + kPairB, kPairB);
           if (Rl.e_slot >= 0) load(ft + (size_t)Rl.e_slot * kImg, kImg);
         } else if (kind == ROLE_Z) {
+          load(src, kPairB);
+          load(src + kPairB, kPairB);
           load(ft + (size_t)Rl.e_slot * kImg, kImg);
         } else {
           load(ft + (size_t)Rl.x_slot * kImg, kPairB);
@@ -205,6 +245,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           load(ft + (size_t)Rl.p_slot[1] * kImg, kPairB);
         }
       }
+      if (P.stats) { atomicAdd(P.stats + role_id * kPipeStatSlots + 0, (unsigned long long)w0); atomicAdd(P.stats + role_id * kPipeStatSlots + 1, (unsigned long long)w1); }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ====================================================
@@ -212,32 +253,113 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc_dg = umma_idesc_bf16(128, 128);
       uint32_t pc = 0;
-      auto use = [&](uint32_t& s) {                      // next pair of the sequence: wait until it has landed
-        s = pc % npairs;
-        mbar_wait(bar_full(s), (pc / npairs) & 1u);
-        ++pc;
-      };
+      auto slot_of = [&](uint32_t& s, uint32_t& ph) { s = pc % npairs; ph = (pc / npairs) & 1u; ++pc; };
       auto kdesc = [&](uint32_t addr) { return umma_desc_sw128(addr); };
       auto mndesc = [&](uint32_t addr) { return umma_desc_mn_sw128(addr, kImg); };
+      // one wgrad product block: D[tmem_col ..] (+)= A(MN-major pair / image)^T-view . B(MN-major), K = 128 samples
+      auto wgrad = [&](uint32_t dcol, uint32_t a_addr, uint32_t b_addr, int ncols, uint32_t first) {
+        const uint32_t idesc = pipe_idesc_mn(128, ncols);
+        const uint64_t a0 = mndesc(a_addr), b0 = mndesc(b_addr);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16(tm + dcol, a0 + (uint64_t)(ks * 128), b0 + (uint64_t)(ks * 128), idesc, (ks == 0) ? first : 1u);
+      };
       if (wt_bytes) mbar_wait(bar_wt, 0);
       for (int64_t i = 0; i < n_my; ++i) {
         const uint32_t first = i == 0 ? 0u : 1u;         // accumulate flag of the launch-long wgrad accumulators
-        uint32_t sA = 0, sB = 0, sC = 0, sE = 0, sP0 = 0, sP1 = 0;
-        if (kind != ROLE_V) {
-          use(sA); use(sB);
-          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + half, 1u);    // this half holds tile i in shared memory
-        }
-        if (kind == ROLE_T || kind == ROLE_V) {
-          // ---- dgrad: D[128 samples x 128] = A[128 x K] . W^T[half]^T --------------------------------
-          mbar_wait(bar_dg_empty, (uint32_t)(i & 1) ^ 1u);
-          if (kind == ROLE_V) mbar_wait(bar_zv_full, (uint32_t)(i & 1));
+        const uint32_t par = (uint32_t)(i & 1);
+        if (kind == ROLE_T) {
+          uint32_t sA, pA, sC, pCc, sB, pB, sE = 0, pE = 0;
+          slot_of(sA, pA); slot_of(sC, pCc); slot_of(sB, pB);
+          if (Rl.e_slot >= 0) slot_of(sE, pE);
+          const PipeProduct& pr = Rl.prod[0];
+          // dgrad over K-blocks 0,1 | wgrad M-block 0 | dgrad over K-blocks 2,3 | wgrad M-block 1: pair A is released at
+          // half time, so the loader's prefetch distance (4 pair slots = 1 1/3 tiles) covers the L2 latency
+          mbar_wait_t(bar_dg_empty, par ^ 1u, w1);
+          mbar_wait_t(bar_full(sA), pA, w0);
           tc_fence_after();
           if (elect_one()) {
-            const int nkb = kind == ROLE_V ? 2 : 4;
-            for (int kb = 0; kb < nkb; ++kb) {
-              const uint32_t img = kind == ROLE_V ? base + off_zv + (uint32_t)kb * kImg
-                                                  : pair_addr(kb < 2 ? sA : sB) + (uint32_t)(kb & 1) * kImg;
-              const uint64_t a = kdesc(img), b = kdesc(base + kPOffWt + (uint32_t)kb * kImg);
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t a = kdesc(pair_addr(sA) + (uint32_t)kb * kImg), b = kdesc(base + kPOffWt + (uint32_t)kb * kImg);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(tm, a + (uint64_t)(2 * ks), b + (uint64_t)(2 * ks), idesc_dg, (kb | ks) ? 1u : 0u);
+            }
+          }
+          __syncwarp();
+          mbar_wait_t(bar_full(sC), pCc, w0);
+          tc_fence_after();
+          if (elect_one()) {
+            wgrad((uint32_t)pr.tmem_col, pair_addr(sA), pair_addr(sC), pr.ncols, first);
+            if (Rl.e_slot < 0) umma_commit(bar_empty(sA));
+          }
+          __syncwarp();
+          mbar_wait_t(bar_full(sB), pB, w0);
+          tc_fence_after();
+          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + half, 1u);    // this half holds tile i in shared memory
+          if (elect_one()) {
+            for (int kb = 2; kb < 4; ++kb) {
+              const uint64_t a = kdesc(pair_addr(sB) + (uint32_t)(kb & 1) * kImg), b = kdesc(base + kPOffWt + (uint32_t)kb * kImg);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(tm, a + (uint64_t)(2 * ks), b + (uint64_t)(2 * ks), idesc_dg, 1u);
+            }
+            umma_commit(bar_dg_full);
+            wgrad((uint32_t)(pr.tmem_col + pr.ncols), pair_addr(sB), pair_addr(sC), pr.ncols, first);
+          }
+          __syncwarp();
+          if (Rl.e_slot >= 0) {                            // L5_0: dW5[:, 0:63] += dZ5^T . PE
+            mbar_wait_t(bar_full(sE), pE, w0);
+            tc_fence_after();
+            if (elect_one()) {
+              const PipeProduct& pe = Rl.prod[1];
+              wgrad((uint32_t)pe.tmem_col, pair_addr(sA), pair_addr(sE), pe.ncols, first);
+              wgrad((uint32_t)(pe.tmem_col + pe.ncols), pair_addr(sB), pair_addr(sE), pe.ncols, first);
+              umma_commit(bar_empty(sA));
+              umma_commit(bar_empty(sE));
+            }
+            __syncwarp();
+          }
+          if (elect_one()) {
+            umma_commit(bar_empty(sC));
+            umma_commit(bar_empty(sB));
+            if (i == n_my - 1) umma_commit(bar_done);
+          }
+          __syncwarp();
+        } else if (kind == ROLE_Z) {
+          uint32_t sA, pA, sB, pB, sE, pE;
+          slot_of(sA, pA); slot_of(sB, pB); slot_of(sE, pE);
+          mbar_wait_t(bar_full(sA), pA, w0);
+          mbar_wait_t(bar_full(sB), pB, w0);
+          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring), 1u);
+          mbar_wait_t(bar_full(sE), pE, w0);
+          tc_fence_after();
+          if (elect_one()) {
+            const PipeProduct& pr = Rl.prod[0];
+            wgrad((uint32_t)pr.tmem_col, pair_addr(sA), pair_addr(sE), pr.ncols, first);
+            wgrad((uint32_t)(pr.tmem_col + pr.ncols), pair_addr(sB), pair_addr(sE), pr.ncols, first);
+            umma_commit(bar_empty(sA)); umma_commit(bar_empty(sB)); umma_commit(bar_empty(sE));
+            if (i == n_my - 1) umma_commit(bar_done);
+          }
+          __syncwarp();
+        } else {
+          uint32_t sC, pCc, sP0, pP0, sP1, pP1;
+          slot_of(sC, pCc); slot_of(sP0, pP0); slot_of(sP1, pP1);
+          // ---- dZv accumulator = G . W_rgb^T (one K = 16 MMA), then the workers mask it into the dZv images ---------
+          mbar_wait_t(bar_g_full, par, w1);
+          tc_fence_after();
+          if (elect_one()) {
+            umma_bf16(tm + 320u, kdesc(base + off_g), kdesc(base + off_wrgb), idesc_dg, 0u);
+            umma_commit(bar_zacc_full);
+          }
+          __syncwarp();
+          // ---- dgrad: dFEAT[:, half] = dZv . Wv[:, half] ----------------------------------------------------
+          mbar_wait_t(bar_dg_empty, par ^ 1u, w1);
+          mbar_wait_t(bar_zv_full, par, w1);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t a = kdesc(base + off_zv + (uint32_t)kb * kImg), b = kdesc(base + kPOffWt + (uint32_t)kb * kImg);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 umma_bf16(tm, a + (uint64_t)(2 * ks), b + (uint64_t)(2 * ks), idesc_dg, (kb | ks) ? 1u : 0u);
@@ -245,80 +367,30 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
             umma_commit(bar_dg_full);
           }
           __syncwarp();
-        }
-        // ---- main wgrad product ----------------------------------------------------------------------
-        if (kind == ROLE_Z) use(sE); else use(sC);
-        tc_fence_after();
-        if (elect_one()) {
-          const PipeProduct& pr = Rl.prod[0];
-          const uint32_t idesc = pipe_idesc_mn(128, pr.ncols);
-          const uint64_t b0 = mndesc(pair_addr(kind == ROLE_Z ? sE : sC));
-          for (int mb = 0; mb < pr.n_mb; ++mb) {
-            const uint64_t a0 = mndesc(kind == ROLE_V ? base + off_zv : pair_addr(mb ? sB : sA));
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              umma_bf16(tm + (uint32_t)(pr.tmem_col + mb * pr.ncols), a0 + (uint64_t)(ks * 128), b0 + (uint64_t)(ks * 128), idesc,
-                        (ks == 0) ? first : 1u);
-          }
-        }
-        __syncwarp();
-        // ---- extra products ----------------------------------------------------------------------------
-        if (kind == ROLE_T && Rl.e_slot >= 0) {            // L5_0: dW5[:, 0:63] += dZ5^T . PE
-          use(sE);
+          mbar_wait_t(bar_full(sC), pCc, w0);
           tc_fence_after();
           if (elect_one()) {
-            const PipeProduct& pr = Rl.prod[1];
-            const uint32_t idesc = pipe_idesc_mn(128, pr.ncols);
-            const uint64_t b0 = mndesc(pair_addr(sE));
-            for (int mb = 0; mb < 2; ++mb) {
-              const uint64_t a0 = mndesc(pair_addr(mb ? sB : sA));
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
-                umma_bf16(tm + (uint32_t)(pr.tmem_col + mb * pr.ncols), a0 + (uint64_t)(ks * 128), b0 + (uint64_t)(ks * 128), idesc,
-                          (ks == 0) ? first : 1u);
-            }
+            wgrad((uint32_t)Rl.prod[0].tmem_col, base + off_zv, pair_addr(sC), Rl.prod[0].ncols, first);
+            umma_commit(bar_empty(sC));
           }
           __syncwarp();
-        }
-        if (kind == ROLE_V) {
-          use(sP0); use(sP1);
-          mbar_wait(bar_g_full, (uint32_t)(i & 1));
+          mbar_wait_t(bar_full(sP0), pP0, w0);
+          mbar_wait_t(bar_full(sP1), pP1, w0);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t g0 = mndesc(base + off_g);
-            {   // prod[1]: V0: rgb head, A = HV pair, B = G image;  V1: dWv[:, 256:283], A = dZv, B = PED image
-              const PipeProduct& pr = Rl.prod[1];
-              const uint32_t idesc = pipe_idesc_mn(128, pr.ncols);
-              const uint64_t a0 = mndesc(Rl.p_slot[0] >= 0 ? pair_addr(sP0) : base + off_zv);
-              const uint64_t b0 = Rl.p_slot[0] >= 0 ? g0 : mndesc(pair_addr(sP0));
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
-                umma_bf16(tm + (uint32_t)pr.tmem_col, a0 + (uint64_t)(ks * 128), b0 + (uint64_t)(ks * 128), idesc, (ks == 0) ? first : 1u);
-            }
-            {   // prod[2]: alpha head for this half of H7: A = H7 pair, B = G image
-              const PipeProduct& pr = Rl.prod[2];
-              const uint32_t idesc = pipe_idesc_mn(128, pr.ncols);
-              const uint64_t a0 = mndesc(pair_addr(sP1));
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
-                umma_bf16(tm + (uint32_t)pr.tmem_col, a0 + (uint64_t)(ks * 128), g0 + (uint64_t)(ks * 128), idesc, (ks == 0) ? first : 1u);
-            }
-          }
-          __syncwarp();
-        }
-        // ---- release everything this tile read ---------------------------------------------------------
-        if (elect_one()) {
-          if (kind != ROLE_V) { umma_commit(bar_empty(sA)); umma_commit(bar_empty(sB)); }
-          if (kind == ROLE_Z) umma_commit(bar_empty(sE)); else umma_commit(bar_empty(sC));
-          if (kind == ROLE_T && Rl.e_slot >= 0) umma_commit(bar_empty(sE));
-          if (kind == ROLE_V) {
+            // prod[1]: V0: rgb head, A = HV pair, B = G image;  V1: dWv[:, 256:283], A = dZv, B = PED image
+            if (Rl.p_slot[0] >= 0) wgrad((uint32_t)Rl.prod[1].tmem_col, pair_addr(sP0), base + off_g, Rl.prod[1].ncols, first);
+            else wgrad((uint32_t)Rl.prod[1].tmem_col, base + off_zv, pair_addr(sP0), Rl.prod[1].ncols, first);
+            // prod[2]: alpha head for this half of H7: A = H7 pair, B = G image
+            wgrad((uint32_t)Rl.prod[2].tmem_col, pair_addr(sP1), base + off_g, Rl.prod[2].ncols, first);
             umma_commit(bar_empty(sP0)); umma_commit(bar_empty(sP1));
             umma_commit(bar_zv_empty); umma_commit(bar_g_empty);
+            if (i == n_my - 1) umma_commit(bar_done);
           }
-          if (i == n_my - 1) umma_commit(bar_done);
+          __syncwarp();
         }
-        __syncwarp();
       }
+      if (P.stats && lane == 0) { atomicAdd(P.stats + role_id * kPipeStatSlots + 2, (unsigned long long)w0); atomicAdd(P.stats + role_id * kPipeStatSlots + 3, (unsigned long long)w1); }
     }
   } else if (warp < 10) {
     // ================================ epilogue warps ================================================
@@ -328,106 +400,89 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     const float* aux = reinterpret_cast<const float*>(P.packed + kSecBOffset);
     float gs0 = 0.f, gs1 = 0.f, gs2 = 0.f, gs3 = 0.f;         // V0: sums of g_raw (head bias gradients)
+    // accumulator columns -> (+ rank-1 term) -> mask -> bf16 -> one swizzled 64-column image row
+    auto emit = [&](const uint32_t (&v)[32], uint32_t mk, uint32_t dst_row, int u, float gsig, const float* wal) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int ii = c * 4 + jj;
+          float lo = __uint_as_float(v[2 * ii]), hi = __uint_as_float(v[2 * ii + 1]);
+          if (wal != nullptr) {
+            lo = fmaf(gsig, __ldg(wal + 2 * ii), lo);
+            hi = fmaf(gsig, __ldg(wal + 2 * ii + 1), hi);
+          }
+          if (!(mk & (1u << ii))) lo = 0.0f;
+          if (!(mk & (1u << (16 + ii)))) hi = 0.0f;
+          pk[jj] = pack_bf16(lo, hi);
+        }
+        const uint32_t c16 = (uint32_t)(u * 4 + c);
+        st_shared_v4(dst_row + ((c16 ^ (row & 7u)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      }
+    };
     if (kind != ROLE_Z) {
       const uint32_t stage_row = base + off_stage + j * kImg + row * 128u;
       for (int64_t i = 0; i < n_my; ++i) {
         const int64_t tile = lane_g + i * kPipeLanes;
         const int64_t g = tile * 128 + row;
+        const uint32_t par = (uint32_t)(i & 1);
         const uint32_t* mtile = P.mask_tape + (size_t)tile * (kMaskUnits * 128) + row;
         float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
         if ((kind == ROLE_V || Rl.rank1) && g < P.M) gr = __ldg(P.g_raw + g);
+        uint32_t v0[32], v1[32];
         if (kind == ROLE_V) {
-          // ---- dZv image j = (g_rgb . W_rgb) (.) [HV > 0], columns [64 j, 64 j + 64) -------------------
-          const float* wrgb = aux + kAuxWRgb;
-          mbar_wait(bar_zv_empty, (uint32_t)(i & 1) ^ 1u);
-          const uint32_t zv_row = base + off_zv + j * kImg + row * 128u;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const uint32_t mb = __ldg(mtile + (kMaskUnitHv + (int)j * 2 + u) * 128);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int ii = c * 4 + jj, col = (int)j * 64 + u * 32 + 2 * ii;
-                float lo = gr.x * __ldg(wrgb + col) + gr.y * __ldg(wrgb + kWV + col) + gr.z * __ldg(wrgb + 2 * kWV + col);
-                float hi = gr.x * __ldg(wrgb + col + 1) + gr.y * __ldg(wrgb + kWV + col + 1) + gr.z * __ldg(wrgb + 2 * kWV + col + 1);
-                if (!(mb & (1u << ii))) lo = 0.0f;
-                if (!(mb & (1u << (16 + ii)))) hi = 0.0f;
-                pk[jj] = pack_bf16(lo, hi);
-              }
-              const uint32_t c16 = (uint32_t)(u * 4 + c);
-              st_shared_v4(zv_row + ((c16 ^ (row & 7u)) << 4), pk[0], pk[1], pk[2], pk[3]);
-            }
+          // ---- the bf16 image of g_raw: A operand of the dZv product, B operand of the two head products ----------
+          const uint32_t mhv0 = __ldg(mtile + (kMaskUnitHv + (int)j * 2) * 128), mhv1 = __ldg(mtile + (kMaskUnitHv + (int)j * 2 + 1) * 128);
+          mbar_wait_t(bar_g_empty, par ^ 1u, w1);
+          if (j == 0) {
+            // k = 0..2: high parts of g_rgb, 3: g_sigma, 4..6: low parts of g_rgb, 7..9: high parts again (see the W_rgb tile)
+            const uint32_t h01 = pack_bf16(gr.x, gr.y), h2s = pack_bf16(gr.z, gr.w);
+            const float hx = __uint_as_float(h01 << 16), hy = __uint_as_float(h01 & 0xFFFF0000u), hz = __uint_as_float(h2s << 16);
+            const uint32_t l01 = pack_bf16(gr.x - hx, gr.y - hy), l2 = pack_bf16(gr.z - hz, 0.0f) & 0xFFFFu;
+            st_shared_v4(base + off_g + row * 128u + ((row & 7u) << 4), h01, h2s, l01, l2 | (h01 << 16));
+            st_shared_v4(base + off_g + row * 128u + (((row & 7u) ^ 1u) << 4), (h01 >> 16) | (h2s << 16), 0u, 0u, 0u);
+            fence_proxy_async_smem();
+            if (half == 0) { gs0 += gr.x; gs1 += gr.y; gs2 += gr.z; gs3 += gr.w; }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_g_full);                 // all 8 warps: also "my reads of the dZv accumulator are done"
+          // ---- dZv image j = accumulator (.) [HV > 0] -----------------------------------------------------------
+          mbar_wait_t(bar_zacc_full, par, w0);
+          tc_fence_after();
+          tmem_ld32(tmem_row + 320u + j * 64u, v0);
+          tmem_ld32(tmem_row + 320u + j * 64u + 32u, v1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_wait_t(bar_zv_empty, par ^ 1u, w1);
+          const uint32_t zv_row = base + off_zv + j * kImg + row * 128u;
+          emit(v0, mhv0, zv_row, 0, 0.0f, nullptr);
+          emit(v1, mhv1, zv_row, 1, 0.0f, nullptr);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_zv_full);
-          if (j == 0) {                                       // the bf16 image of g_raw the head products multiply with
-            mbar_wait(bar_g_empty, (uint32_t)(i & 1) ^ 1u);
-            // logical 16-byte chunks 0 and 1 of the row (N = 16 columns are multiplied): (g_r, g_g, g_b, g_sigma, 0 ...)
-            st_shared_v4(base + off_g + row * 128u + ((row & 7u) << 4), pack_bf16(gr.x, gr.y), pack_bf16(gr.z, gr.w), 0u, 0u);
-            st_shared_v4(base + off_g + row * 128u + (((row & 7u) ^ 1u) << 4), 0u, 0u, 0u, 0u);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_g_full);
-            if (half == 0) { gs0 += gr.x; gs1 += gr.y; gs2 += gr.z; gs3 += gr.w; }
-          }
         }
         // ---- dgrad epilogue: accumulator -> (+ rank-1 sigma term) -> ReLU mask -> bf16 -> staging image j -----
-        uint32_t mk[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        uint32_t mk0 = 0xFFFFFFFFu, mk1 = 0xFFFFFFFFu;
         if (Rl.mask_unit0 >= 0) {
-          mk[0] = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2) * 128);
-          mk[1] = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2 + 1) * 128);
+          mk0 = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2) * 128);
+          mk1 = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2 + 1) * 128);
         }
-        mbar_wait(bar_dg_full, (uint32_t)(i & 1));
+        mbar_wait_t(bar_dg_full, par, w0);
         tc_fence_after();
-        uint32_t v0[32], v1[32];
         tmem_ld32(tmem_row + j * 64u, v0);
         tmem_ld32(tmem_row + j * 64u + 32u, v1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_dg_empty);               // the accumulator may be overwritten by the next tile
-        group_bar(2u + j, 128u);                                // the previous store of this staging image has read it
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const uint32_t* v = u ? v1 : v0;
-          const int col0 = half * 128 + (int)j * 64 + u * 32;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int ii = c * 4 + jj;
-              float lo = __uint_as_float(v[2 * ii]), hi = __uint_as_float(v[2 * ii + 1]);
-              if (Rl.rank1) {
-                lo = fmaf(gr.w, __ldg(aux + kAuxWAlpha + col0 + 2 * ii), lo);
-                hi = fmaf(gr.w, __ldg(aux + kAuxWAlpha + col0 + 2 * ii + 1), hi);
-              }
-              if (!(mk[u] & (1u << ii))) lo = 0.0f;
-              if (!(mk[u] & (1u << (16 + ii)))) hi = 0.0f;
-              pk[jj] = pack_bf16(lo, hi);
-            }
-            const uint32_t c16 = (uint32_t)(u * 4 + c);
-            st_shared_v4(stage_row + ((c16 ^ (row & 7u)) << 4), pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
+        mbar_wait_t(bar_img_empty(j), par ^ 1u, w2);            // the store of the previous tile has read the staging image
+        const float* wal = Rl.rank1 ? aux + kAuxWAlpha + half * 128 + (int)j * 64 : nullptr;
+        emit(v0, mk0, stage_row, 0, gr.w, wal);
+        emit(v1, mk1, stage_row, 1, gr.w, wal ? wal + 32 : nullptr);
         fence_proxy_async_smem();
-        group_bar(4u + j, 128u);                                // image j of this tile is complete in shared memory
-        if (q == 0 && lane == 0) {
-          // hand image 2*half + j of tile i to the next layer: ring slot free? -> bulk store -> publish
-          if (i >= kPipeDepth) {                              // every consumer half has tile i - depth in its shared memory
-            spin_until_ge(done + flag_idx(Rl.out_ring), (uint32_t)(i - kPipeDepth + 1));
-            if (Rl.out_ring != kPipeRings - 1) spin_until_ge(done + flag_idx(Rl.out_ring) + 1, (uint32_t)(i - kPipeDepth + 1));
-          }
-          bulk_s2g(ring_tile(Rl.out_ring, i) + (size_t)(2 * half + (int)j) * kImg, base + off_stage + j * kImg, kImg);
-          bulk_commit();
-          bulk_wait_all<0>();
-          fence_proxy_async_global();
-          __threadfence();
-          red_release_gpu_add(ready + flag_idx(Rl.out_ring) + half, 1u);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_img_full(j));
       }
     }
     // ---- flush the launch-long weight-gradient accumulators -------------------------------------------
@@ -472,11 +527,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           atomicAdd(P.flat_grad + flat_bias_offset(8, P.cond), gs3);
         }
       }
+      if (P.stats && lane == 0) {
+        atomicAdd(P.stats + role_id * kPipeStatSlots + 4, (unsigned long long)w0); atomicAdd(P.stats + role_id * kPipeStatSlots + 5, (unsigned long long)w1);
+        atomicAdd(P.stats + role_id * kPipeStatSlots + 6, (unsigned long long)w2);
+      }
     }
-  } else {
+  } else if (warp < 14) {
     // ================================ bias warps ====================================================
     // column sums of the incoming gradient images (bias gradients), accumulated in registers over the launch: thread e
-    // owns the column pair (2p, 2p+1) of image `im` over the rows [64 rh, 64 rh + 64)
+    // owns the column pair (2p, 2p+1) of one image over a block of rows
     const int e = (int)threadIdx.x - 320;                 // 0..127
     const uint32_t p = (uint32_t)e & 31u;
     const int sel = e >> 5;                               // warp of the four
@@ -496,8 +555,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         const uint32_t s = pc % npairs;
         mbar_wait(bar_full(s), (pc / npairs) & 1u);
         const uint8_t* pair = base_ptr + off_ring + s * kPairB;
-        if (kind == ROLE_T && k == half) {
-          // images {2 half, 2 half + 1} of dZ: warp sel -> image sel / 2, rows half sel % 2
+        if (kind == ROLE_T && k == (half ? 2 : 0)) {
+          // images {2 half, 2 half + 1} of dZ (pair A or B): warp sel -> image sel / 2, rows half sel % 2
           colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, b0, b1);
         } else if (kind == ROLE_Z && k < 2) {
           // all four images: pair k, warp sel -> image sel / 2 of the pair, rows half sel % 2
@@ -528,6 +587,48 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         atomicAdd(dst, b0); atomicAdd(dst + 1, b1);
       }
     }
+  } else {
+    // ================================ ring stores ===================================================
+    // warp 14 + j hands image 2*half + j of every tile to the next layer: bulk store from the staging image, then the
+    // `ready` counter.  The staging image is released as soon as the store has READ it; the counter is published when the
+    // store has COMPLETED, which is only awaited once the next tile's store is in flight (or at once, when no next image
+    // is waiting), so the global write latency is off the per-tile critical path.
+    const uint32_t j = (uint32_t)warp - 14u;
+    if (lane == 0 && kind != ROLE_Z && n_my > 0) {
+      int64_t published = 0;
+      uint32_t* rdy = ready + flag_idx(Rl.out_ring) + half;
+      auto publish_upto = [&](int64_t n) {                     // tiles [published, n) have completed their stores
+        if (n > published) {
+          fence_proxy_async_global();
+          __threadfence();
+          red_release_gpu_add(rdy, (uint32_t)(n - published));
+          published = n;
+        }
+      };
+      for (int64_t i = 0; i < n_my; ++i) {
+        const uint32_t par = (uint32_t)(i & 1);
+        if (!mbar_test_wait(bar_img_full(j), par)) {           // nothing to store yet: drain and publish what is in flight
+          bulk_wait_all<0>();
+          publish_upto(i);
+          mbar_wait_t(bar_img_full(j), par, w0);
+        }
+        if (i >= kPipeDepth) {                                 // every consumer half has tile i - depth in its shared memory
+          const long long t0 = clock64();
+          spin_until_ge(done + flag_idx(Rl.out_ring), (uint32_t)(i - kPipeDepth + 1));
+          if (Rl.out_ring != kPipeRings - 1) spin_until_ge(done + flag_idx(Rl.out_ring) + 1, (uint32_t)(i - kPipeDepth + 1));
+          w1 += clock64() - t0;
+        }
+        bulk_s2g(ring_tile(Rl.out_ring, i) + (size_t)(2 * half + (int)j) * kImg, base + off_stage + j * kImg, kImg);
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(bar_img_empty(j));
+        bulk_wait_all<1>();                                    // every store but the newest has completed
+        publish_upto(i);
+      }
+      bulk_wait_all<0>();
+      publish_upto(n_my);
+      if (P.stats && j == 0) { atomicAdd(P.stats + role_id * kPipeStatSlots + 7, (unsigned long long)w0); }
+    }
   }
 
   tc_fence_before();
@@ -537,6 +638,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+static unsigned long long* g_pipe_stats = nullptr;     // debug: device buffer [kPipeRoles][kPipeStatSlots], see fnerf_debug_pipe_stats
 
 int64_t mlp_bwd_pipe_workspace_bytes() {
   return (int64_t)kPipeRings * kPipeLanes * kPipeDepth * kTileB + 2 * (int64_t)kPipeRings * kPipeLanes * 32 * 4 + 1024;
@@ -559,6 +662,7 @@ int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape
   P.ring = w8;
   P.flags = reinterpret_cast<uint32_t*>(w8 + (int64_t)kPipeRings * kPipeLanes * kPipeDepth * kTileB);
   P.flat_grad = flat_grad; P.M = M; P.ntiles = ntiles;
+  P.stats = g_pipe_stats;
   auto gw = [&](int l) { return flat_grad + flat_weight_offset(l, cond); };
   auto gb = [&](int l) { return flat_grad + flat_bias_offset(l, cond); };
   const int in5 = kPE + kW;
@@ -624,3 +728,11 @@ int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape
 }
 
 }  // namespace fnerf
+
+// ---- debug entry (tools only): every following pipelined backward adds, per role, the cycles its warps spent waiting
+// into stats[role * 8 + slot] (slots: loader ring flags / free slots, MMA operands / accumulators, epilogue accumulators /
+// buffers / staging, store warp images).  NULL switches the accounting off.
+extern "C" int fnerf_debug_pipe_stats(unsigned long long* stats) {
+  fnerf::g_pipe_stats = stats;
+  return fnerf::kPipeRoles * fnerf::kPipeStatSlots;
+}
