@@ -16,45 +16,6 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// Sum of five per-lane values over the warp in 8 shuffles instead of 25: at every butterfly step a lane keeps only the
-// values its half of the warp is responsible for and sends the others.  On return lane 0 holds the sum of v0, lane 8 of
-// v1, lane 16 of v2, lane 24 of v3 and lane 4 of v4 (every lane with the same (lane & 28) holds the same value).
-__device__ __forceinline__ float warp_sum5(float v0, float v1, float v2, float v3, float v4, int lane) {
-  // xor 16: lanes < 16 keep (v0, v1, v4), lanes >= 16 keep (v2, v3)
-  const bool hi16 = lane & 16;
-  float a = hi16 ? v2 : v0, b = hi16 ? v3 : v1;                  // kept
-  float sa = hi16 ? v0 : v2, sb = hi16 ? v1 : v3;                // sent
-  a += __shfl_xor_sync(0xffffffffu, sa, 16);
-  b += __shfl_xor_sync(0xffffffffu, sb, 16);
-  float c = v4 + __shfl_xor_sync(0xffffffffu, v4, 16);           // v4: plain butterfly for this step (both halves hold it)
-  // xor 8: within each half, lanes with bit 3 clear keep a, the others keep b
-  const bool hi8 = lane & 8;
-  float k = hi8 ? b : a, snd = hi8 ? a : b;
-  k += __shfl_xor_sync(0xffffffffu, snd, 8);
-  c += __shfl_xor_sync(0xffffffffu, c, 8);
-  // xor 4: lanes with bit 2 clear keep k, lanes with bit 2 set take over c (all hold the same partial c)
-  const bool hi4 = lane & 4;
-  float m = hi4 ? c : k, snd2 = hi4 ? k : c;
-  m += __shfl_xor_sync(0xffffffffu, snd2, 4);
-  m += __shfl_xor_sync(0xffffffffu, m, 2);
-  m += __shfl_xor_sync(0xffffffffu, m, 1);
-  return m;      // lanes 0-3: v0, 8-11: v1, 16-19: v2, 24-27: v3;  lanes 4-7, 12-15, 20-23, 28-31: v4
-}
-// the maps of one ray from the five weighted sums (rgb, depth, acc): lanes 0 / 8 / 16 write the colour channels, lane 24
-// depth and disparity, lane 4 the accumulated opacity
-__device__ __forceinline__ void write_maps(float a_r, float a_g, float a_b, float a_d, float a_w, int lane, int64_t r, int white,
-                                           float* __restrict__ rgb_out, float* __restrict__ depth_out,
-                                           float* __restrict__ acc_out, float* __restrict__ disp_out) {
-  const float m = warp_sum5(a_r, a_g, a_b, a_d, a_w, lane);
-  const float acc = __shfl_sync(0xffffffffu, m, 4);
-  if (lane == 0 || lane == 8 || lane == 16) rgb_out[3 * r + (lane >> 3)] = m + (white ? (1.0f - acc) : 0.0f);
-  if (lane == 4) acc_out[r] = m;
-  if (lane == 24) {
-    depth_out[r] = m;
-    const float q = m / acc;                  // NaN when acc == 0: propagated like torch.max does
-    disp_out[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
-  }
-}
 // sigmoid through ex2.approx + rcp-based division (~6 instructions instead of ~30): relative error ~3e-7, which
 // enters the maps linearly (weights sum to <= 1); the transmittance product keeps the exact expf
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -136,7 +97,18 @@ k_composite_fwd(const float4* __restrict__ raw, const float* __restrict__ z,
       }
       rv = rv_n; zv = zv_n; nz = nz_n; i = inext;
     }
-    write_maps(a_r, a_g, a_b, a_d, a_w, lane, r, white, rgb_out, depth_out, acc_out, disp_out);
+    a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);
+    a_d = warp_sum(a_d); a_w = warp_sum(a_w);
+    if (lane == 0) {
+      const float bg = white ? (1.0f - a_w) : 0.0f;
+      rgb_out[3 * r] = a_r + bg;
+      rgb_out[3 * r + 1] = a_g + bg;
+      rgb_out[3 * r + 2] = a_b + bg;
+      depth_out[r] = a_d;
+      acc_out[r] = a_w;
+      const float q = a_d / a_w;              // NaN when acc == 0: propagated like torch.max does
+      disp_out[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
+    }
   }
 }
 
@@ -200,7 +172,18 @@ k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
         }
       }
     }
-    write_maps(a_r, a_g, a_b, a_d, a_w, lane, r, white, rgb_out, depth_out, acc_out, disp_out);
+    a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);
+    a_d = warp_sum(a_d); a_w = warp_sum(a_w);
+    if (lane == 0) {
+      const float bg = white ? (1.0f - a_w) : 0.0f;
+      rgb_out[3 * r] = a_r + bg;
+      rgb_out[3 * r + 1] = a_g + bg;
+      rgb_out[3 * r + 2] = a_b + bg;
+      depth_out[r] = a_d;
+      acc_out[r] = a_w;
+      const float q = a_d / a_w;              // NaN when acc == 0: propagated like torch.max does
+      disp_out[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
+    }
   }
 }
 

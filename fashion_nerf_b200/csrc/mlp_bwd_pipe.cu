@@ -33,7 +33,7 @@ namespace fnerf {
 using namespace ptx;
 
 constexpr int kPipeLanes = 7;
-constexpr int kPipeRoles = 19;                 // V0 V1 F0 F1 L7_0 L7_1 ... L1_0 L1_1 L0
+constexpr int kPipeRoles = 21;                 // V0a V0b V1a V1b F0 F1 L7_0 L7_1 ... L1_0 L1_1 L0
 constexpr int kPipeRings = 9;                  // V->F, F->L7, L7->L6, ..., L1->L0
 constexpr int kPipeDepth = 8;                  // tiles per ring (covers the store -> flag -> poll -> load round trip)
 constexpr int kPipeThreads = 512;              // warps: 0 loader, 1 MMA, 2..9 epilogue, 10..13 bias sums, 14..15 ring stores
@@ -59,6 +59,7 @@ struct PipeProduct {            // one weight-gradient product accumulated in TM
 };
 struct PipeRole {
   int kind, half;
+  int t0, tstep;                // the role runs the lane's tiles t0, t0 + tstep, ... (view roles: two CTAs alternate)
   int in_ring, out_ring;        // -1: none
   int wt_chunk0, wt_nchunks;    // section E chunks of W^T (rows [128*half, +128) of each)
   int x_slot;                   // forward-tape slot of the activation pair (X operand of the main wgrad product)
@@ -125,7 +126,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
   const PipeRole& Rl = P.roles[role_id];
   const int kind = Rl.kind, half = Rl.half;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_my = P.ntiles > lane_g ? (P.ntiles - lane_g + kPipeLanes - 1) / kPipeLanes : 0;   // tiles of this lane
+  const int64_t n_lane = P.ntiles > lane_g ? (P.ntiles - lane_g + kPipeLanes - 1) / kPipeLanes : 0;   // tiles of this lane
+  const int64_t t0 = Rl.t0, tstep = Rl.tstep;                                 // ... of which this CTA runs i = t0, t0 + tstep, ...
+  const bool has_work = t0 < n_lane;
 
   // ---- shared-memory map --------------------------------------------------------------------------
   const uint32_t wt_bytes = (uint32_t)Rl.wt_nchunks * kImg;                       // 64 KB (trunk), 32 KB (view), 0 (L0)
@@ -188,6 +191,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
   uint32_t* ready = P.flags;
   uint32_t* done = P.flags + kPipeRings * kPipeLanes * 32;
   auto flag_idx = [&](int ring) { return (ring * kPipeLanes + lane_g) * 32; };
+  // `ready` counters: one per producing CTA of a ring = (half, tile parity for ring 0 whose producers alternate); a
+  // counter counts the images its CTA has published, two per tile
+  auto wait_ready = [&](int ring, int64_t i) {
+    const int np = ring == 0 ? 2 : 1;
+    const uint32_t* c = ready + flag_idx(ring) + (int)(i % np);
+    const uint32_t target = (uint32_t)(2 * (i / np + 1));
+    spin_until_ge(c, target);
+    spin_until_ge(c + 2, target);
+  };
   auto ring_tile = [&](int ring, int64_t i) {
     return P.ring + ((size_t)(ring * kPipeLanes + lane_g) * kPipeDepth + (size_t)(i % kPipeDepth)) * kTileB;
   };
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
 
   if (warp == 0) {
     // ================================ loader ========================================================
-    if (lane == 0 && n_my > 0) {
+    if (lane == 0 && has_work) {
       if (wt_bytes) {                                   // stationary W^T half: rows [128*half, +128) of every chunk
         mbar_expect_tx(bar_wt, wt_bytes);
         const uint8_t* wsrc = P.packed + sec_e_offset(P.cond);
@@ -216,16 +228,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         bulk_g2s(pair_addr(s), src, bytes, bar_full(s));
         ++pc;
       };
-      for (int64_t i = 0; i < n_my; ++i) {
+      for (int64_t i = t0; i < n_lane; i += tstep) {
         const int64_t tile = lane_g + i * kPipeLanes;
         const uint8_t* ft = P.fwd_tape + tile * fstride;
         const uint8_t* src = nullptr;
         if (kind != ROLE_V) {
           // both halves of the producing layer have published their two images of tile i
-          const long long t0 = clock64();
-          spin_until_ge(ready + flag_idx(Rl.in_ring), (uint32_t)(2 * (i + 1)));
-          spin_until_ge(ready + flag_idx(Rl.in_ring) + 1, (uint32_t)(2 * (i + 1)));
-          w0 += clock64() - t0;
+          const long long c0 = clock64();
+          wait_ready(Rl.in_ring, i);
+          w0 += clock64() - c0;
           fence_proxy_async_global();
           src = ring_tile(Rl.in_ring, i);
         }
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ====================================================
-    if (n_my > 0) {
+    if (has_work) {
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc_dg = umma_idesc_bf16(128, 128);
       uint32_t pc = 0;
@@ -265,9 +276,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           umma_bf16(tm + dcol, a0 + (uint64_t)(ks * 128), b0 + (uint64_t)(ks * 128), idesc, (ks == 0) ? first : 1u);
       };
       if (wt_bytes) mbar_wait(bar_wt, 0);
-      for (int64_t i = 0; i < n_my; ++i) {
-        const uint32_t first = i == 0 ? 0u : 1u;         // accumulate flag of the launch-long wgrad accumulators
-        const uint32_t par = (uint32_t)(i & 1);
+      int64_t kk = 0;
+      for (int64_t i = t0; i < n_lane; i += tstep, ++kk) {
+        const uint32_t first = kk == 0 ? 0u : 1u;        // accumulate flag of the launch-long wgrad accumulators
+        const uint32_t par = (uint32_t)(kk & 1);
+        const bool last = i + tstep >= n_lane;
         if (kind == ROLE_T) {
           uint32_t sA, pA, sC, pCc, sB, pB, sE = 0, pE = 0;
           slot_of(sA, pA); slot_of(sC, pCc); slot_of(sB, pB);
@@ -296,7 +309,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           __syncwarp();
           mbar_wait_t(bar_full(sB), pB, w0);
           tc_fence_after();
-          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + half, 1u);    // this half holds tile i in shared memory
+          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + 2 * half, 1u);    // this half holds tile i in shared memory
           if (elect_one()) {
             for (int kb = 2; kb < 4; ++kb) {
               const uint64_t a = kdesc(pair_addr(sB) + (uint32_t)(kb & 1) * kImg), b = kdesc(base + kPOffWt + (uint32_t)kb * kImg);
@@ -323,7 +336,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           if (elect_one()) {
             umma_commit(bar_empty(sC));
             umma_commit(bar_empty(sB));
-            if (i == n_my - 1) umma_commit(bar_done);
+            if (last) umma_commit(bar_done);
           }
           __syncwarp();
         } else if (kind == ROLE_Z) {
@@ -339,7 +352,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
             wgrad((uint32_t)pr.tmem_col, pair_addr(sA), pair_addr(sE), pr.ncols, first);
             wgrad((uint32_t)(pr.tmem_col + pr.ncols), pair_addr(sB), pair_addr(sE), pr.ncols, first);
             umma_commit(bar_empty(sA)); umma_commit(bar_empty(sB)); umma_commit(bar_empty(sE));
-            if (i == n_my - 1) umma_commit(bar_done);
+            if (last) umma_commit(bar_done);
           }
           __syncwarp();
         } else {
@@ -385,7 +398,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
             wgrad((uint32_t)Rl.prod[2].tmem_col, pair_addr(sP1), base + off_g, Rl.prod[2].ncols, first);
             umma_commit(bar_empty(sP0)); umma_commit(bar_empty(sP1));
             umma_commit(bar_zv_empty); umma_commit(bar_g_empty);
-            if (i == n_my - 1) umma_commit(bar_done);
+            if (last) umma_commit(bar_done);
           }
           __syncwarp();
         }
@@ -423,17 +436,39 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     };
     if (kind != ROLE_Z) {
       const uint32_t stage_row = base + off_stage + j * kImg + row * 128u;
-      for (int64_t i = 0; i < n_my; ++i) {
+      // per-tile global inputs (g_raw row, ReLU-mask words) are fetched ONE TILE AHEAD: on the tile's own critical path
+      // their DRAM latency (~1 us) was the longest link of the view roles' chain
+      struct TileIn { float4 gr; uint32_t mk0, mk1, mhv0, mhv1; };
+      auto fetch = [&](int64_t i) {
+        TileIn t;
+        t.gr = make_float4(0.f, 0.f, 0.f, 0.f);
+        t.mk0 = t.mk1 = 0xFFFFFFFFu; t.mhv0 = t.mhv1 = 0u;
+        if (i >= n_lane) return t;
         const int64_t tile = lane_g + i * kPipeLanes;
         const int64_t g = tile * 128 + row;
-        const uint32_t par = (uint32_t)(i & 1);
         const uint32_t* mtile = P.mask_tape + (size_t)tile * (kMaskUnits * 128) + row;
-        float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((kind == ROLE_V || Rl.rank1) && g < P.M) gr = __ldg(P.g_raw + g);
+        if ((kind == ROLE_V || Rl.rank1) && g < P.M) t.gr = __ldg(P.g_raw + g);
+        if (Rl.mask_unit0 >= 0) {
+          t.mk0 = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2) * 128);
+          t.mk1 = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2 + 1) * 128);
+        }
+        if (kind == ROLE_V) {
+          t.mhv0 = __ldg(mtile + (kMaskUnitHv + (int)j * 2) * 128);
+          t.mhv1 = __ldg(mtile + (kMaskUnitHv + (int)j * 2 + 1) * 128);
+        }
+        return t;
+      };
+      TileIn nxt = fetch(t0);
+      int64_t kk = 0;
+      for (int64_t i = t0; i < n_lane; i += tstep, ++kk) {
+        const uint32_t par = (uint32_t)(kk & 1);
+        const TileIn cur = nxt;
+        nxt = fetch(i + tstep);
+        const float4 gr = cur.gr;
         uint32_t v0[32], v1[32];
         if (kind == ROLE_V) {
           // ---- the bf16 image of g_raw: A operand of the dZv product, B operand of the two head products ----------
-          const uint32_t mhv0 = __ldg(mtile + (kMaskUnitHv + (int)j * 2) * 128), mhv1 = __ldg(mtile + (kMaskUnitHv + (int)j * 2 + 1) * 128);
+          const uint32_t mhv0 = cur.mhv0, mhv1 = cur.mhv1;
           mbar_wait_t(bar_g_empty, par ^ 1u, w1);
           if (j == 0) {
             // k = 0..2: high parts of g_rgb, 3: g_sigma, 4..6: low parts of g_rgb, 7..9: high parts again (see the W_rgb tile)
@@ -463,11 +498,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           if (lane == 0) mbar_arrive(bar_zv_full);
         }
         // ---- dgrad epilogue: accumulator -> (+ rank-1 sigma term) -> ReLU mask -> bf16 -> staging image j -----
-        uint32_t mk0 = 0xFFFFFFFFu, mk1 = 0xFFFFFFFFu;
-        if (Rl.mask_unit0 >= 0) {
-          mk0 = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2) * 128);
-          mk1 = __ldg(mtile + (Rl.mask_unit0 + (int)j * 2 + 1) * 128);
-        }
+        const uint32_t mk0 = cur.mk0, mk1 = cur.mk1;
         mbar_wait_t(bar_dg_full, par, w0);
         tc_fence_after();
         tmem_ld32(tmem_row + j * 64u, v0);
@@ -486,7 +517,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
       }
     }
     // ---- flush the launch-long weight-gradient accumulators -------------------------------------------
-    if (n_my > 0) {
+    if (has_work) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
       for (int p = 0; p < Rl.nprod; ++p) {
@@ -550,7 +581,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
       }
     };
     uint32_t pc = 0;
-    for (int64_t i = 0; i < n_my; ++i) {
+    int64_t kk = 0;
+    for (int64_t i = t0; i < n_lane; i += tstep, ++kk) {
       for (int k = 0; k < n_seq; ++k, ++pc) {
         const uint32_t s = pc % npairs;
         mbar_wait(bar_full(s), (pc / npairs) & 1u);
@@ -567,14 +599,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         if (lane == 0) mbar_arrive(bar_empty(s));
       }
       if (kind == ROLE_V) {
-        mbar_wait(bar_zv_full, (uint32_t)(i & 1));
+        mbar_wait(bar_zv_full, (uint32_t)(kk & 1));
         // dZv image `half`: 64 columns = 32 pairs; warp sel sums rows [32 sel, +32)
         colsum(base_ptr + off_zv + (uint32_t)half * kImg, (uint32_t)sel * 32u, 32u, b0, b1);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_zv_empty);
       }
     }
-    if (n_my > 0 && Rl.bias != nullptr) {
+    if (has_work && Rl.bias != nullptr) {
       if (kind == ROLE_T) {
         float* dst = Rl.bias + half * 128 + (sel >> 1) * 64 + 2 * (int)p;
         atomicAdd(dst, b0); atomicAdd(dst + 1, b1);
@@ -594,9 +626,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     // store has COMPLETED, which is only awaited once the next tile's store is in flight (or at once, when no next image
     // is waiting), so the global write latency is off the per-tile critical path.
     const uint32_t j = (uint32_t)warp - 14u;
-    if (lane == 0 && kind != ROLE_Z && n_my > 0) {
-      int64_t published = 0;
-      uint32_t* rdy = ready + flag_idx(Rl.out_ring) + half;
+    if (lane == 0 && kind != ROLE_Z && has_work) {
+      int64_t published = 0;                                   // in units of this CTA's tiles
+      uint32_t* rdy = ready + flag_idx(Rl.out_ring) + 2 * half + (int)t0;
       auto publish_upto = [&](int64_t n) {                     // tiles [published, n) have completed their stores
         if (n > published) {
           fence_proxy_async_global();
@@ -605,28 +637,29 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           published = n;
         }
       };
-      for (int64_t i = 0; i < n_my; ++i) {
-        const uint32_t par = (uint32_t)(i & 1);
+      int64_t kk = 0;
+      for (int64_t i = t0; i < n_lane; i += tstep, ++kk) {
+        const uint32_t par = (uint32_t)(kk & 1);
         if (!mbar_test_wait(bar_img_full(j), par)) {           // nothing to store yet: drain and publish what is in flight
           bulk_wait_all<0>();
-          publish_upto(i);
+          publish_upto(kk);
           mbar_wait_t(bar_img_full(j), par, w0);
         }
         if (i >= kPipeDepth) {                                 // every consumer half has tile i - depth in its shared memory
-          const long long t0 = clock64();
+          const long long c0 = clock64();
           spin_until_ge(done + flag_idx(Rl.out_ring), (uint32_t)(i - kPipeDepth + 1));
-          if (Rl.out_ring != kPipeRings - 1) spin_until_ge(done + flag_idx(Rl.out_ring) + 1, (uint32_t)(i - kPipeDepth + 1));
-          w1 += clock64() - t0;
+          if (Rl.out_ring != kPipeRings - 1) spin_until_ge(done + flag_idx(Rl.out_ring) + 2, (uint32_t)(i - kPipeDepth + 1));
+          w1 += clock64() - c0;
         }
         bulk_s2g(ring_tile(Rl.out_ring, i) + (size_t)(2 * half + (int)j) * kImg, base + off_stage + j * kImg, kImg);
         bulk_commit();
         bulk_wait_read<0>();
         mbar_arrive(bar_img_empty(j));
         bulk_wait_all<1>();                                    // every store but the newest has completed
-        publish_upto(i);
+        publish_upto(kk);
       }
       bulk_wait_all<0>();
-      publish_upto(n_my);
+      publish_upto(kk);
       if (P.stats && j == 0) { atomicAdd(P.stats + role_id * kPipeStatSlots + 7, (unsigned long long)w0); }
     }
   }
@@ -671,9 +704,12 @@ int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape
     PipeProduct p; p.dw = dw; p.ld_n = ld_n; p.ld_k = ld_k; p.tmem_col = tmem_col; p.n_mb = n_mb; p.ncols = ncols; p.k0 = k0; p.n_valid = n_valid;
     return p;
   };
-  // V0 / V1
-  for (int h = 0; h < 2; ++h) {
+  // V0a V0b V1a V1b: per half two CTAs that alternate over the lane's tiles (the view roles' per-tile chain -- g_raw image,
+  // dZv product, mask, dgrad, epilogue -- is serial and about twice as long as a trunk role's tile)
+  for (int hp = 0; hp < 4; ++hp) {
+    const int h = hp >> 1;
     PipeRole& R = P.roles[r++];
+    R.t0 = hp & 1; R.tstep = 2;
     R.kind = ROLE_V; R.half = h; R.in_ring = -1; R.out_ring = 0; R.wt_chunk0 = 0; R.wt_nchunks = 2;
     R.x_slot = kTapeSlotFeat + 2 * h; R.mask_unit0 = -1; R.rank1 = 0;
     R.bias = gb(10);
@@ -693,6 +729,7 @@ int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape
     const int layer = st == 1 ? 9 : 9 - st;                                      // flat layer id: 9 = feature, then 7..1
     for (int h = 0; h < 2; ++h) {
       PipeRole& R = P.roles[r++];
+      R.t0 = 0; R.tstep = 1;
       R.kind = ROLE_T; R.half = h; R.in_ring = st - 1; R.out_ring = st;
       R.wt_chunk0 = st == 1 ? 2 : 6 + 4 * (st - 2); R.wt_nchunks = 4;
       const int hsrc = st == 1 ? 7 : layer - 1;                                  // forward activation H_hsrc is the X operand and the mask
@@ -713,6 +750,7 @@ int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape
   }
   {
     PipeRole& R = P.roles[r++];
+    R.t0 = 0; R.tstep = 1;
     R.kind = ROLE_Z; R.half = 0; R.in_ring = 8; R.out_ring = -1; R.wt_chunk0 = 0; R.wt_nchunks = 0; R.x_slot = 0;
     R.mask_unit0 = -1; R.rank1 = 0; R.e_slot = kTapeSlotPe; R.p_slot[0] = R.p_slot[1] = -1;
     R.bias = gb(0);

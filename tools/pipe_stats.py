@@ -25,7 +25,7 @@ e1.record()
 torch.cuda.synchronize()
 lib.fnerf_debug_pipe_stats(None)
 print(f"step {e0.elapsed_time(e1):.3f} ms (coarse + fine backward accumulated below; 7 CTAs per role; Mcycles)")
-names = ["V0", "V1", "F0", "F1"] + [f"L{l}_{h}" for l in range(7, 0, -1) for h in (0, 1)] + ["L0"]
+names = ["V0a", "V0b", "V1a", "V1b", "F0", "F1"] + [f"L{l}_{h}" for l in range(7, 0, -1) for h in (0, 1)] + ["L0"]
 hdr = ["ld:ring", "ld:slot", "mma:opnd", "mma:acc", "epi:acc", "epi:buf", "epi:stage", "st:img"]
 print(f"{'role':6s}" + "".join(f"{h:>10s}" for h in hdr))
 s = stats.view(-1, 8).cpu()
