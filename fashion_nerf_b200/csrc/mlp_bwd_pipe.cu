@@ -36,6 +36,12 @@ constexpr int kPipeLanes = 7;
 constexpr int kPipeRoles = 21;                 // V0a V0b V1a V1b F0 F1 L7_0 L7_1 ... L1_0 L1_1 L0
 constexpr int kPipeRings = 9;                  // V->F, F->L7, L7->L6, ..., L1->L0
 constexpr int kPipeDepth = 8;                  // tiles per ring (covers the store -> flag -> poll -> load round trip)
+constexpr int kZLag = 12;                      // the L0 role consumes dZ0 of tile i - kZLag right after dZ5 of tile i ...
+constexpr int kPipeDepthLast = 24;             // ... so the last ring (L1 -> L0) holds that many tiles more
+constexpr int kRingZ5 = 3;                     // ring L6 -> L5 (dZ5): third consumer = the L0 role (dW5[:, 0:63])
+__host__ __device__ constexpr int ring_depth(int r) { return r == kPipeRings - 1 ? kPipeDepthLast : kPipeDepth; }
+__host__ __device__ constexpr int64_t ring_first_tile(int r) { return (int64_t)r * kPipeLanes * kPipeDepth; }   // rings 0..r-1 are kPipeDepth deep
+constexpr int64_t kRingTiles = ring_first_tile(kPipeRings - 1) + (int64_t)kPipeLanes * kPipeDepthLast;
 constexpr int kPipeThreads = 512;              // warps: 0 loader, 1 MMA, 2..9 epilogue, 10..13 bias sums, 14..15 ring stores
 constexpr uint32_t kImg = 16384, kPairB = 32768, kTileB = 65536;
 constexpr int kMaxPairs = 4;
@@ -46,7 +52,9 @@ constexpr int kMaxPairs = 4;
 constexpr uint32_t kPOffWt = 0;
 constexpr uint32_t kPOffBar = 229376;
 constexpr uint32_t kPNumBars = 2 * kMaxPairs + 14;
-constexpr uint32_t kPipeSmem = kPOffBar + kPNumBars * 8 + 16 + 1024;
+constexpr uint32_t kPOffWal = kPOffBar + 256;      // F roles: w_alpha[half] (128 fp32) for the rank-1 sigma term
+static_assert(kPNumBars * 8 + 16 <= 256, "barrier block");
+constexpr uint32_t kPipeSmem = kPOffWal + 512 + 1024;
 static_assert(kPipeSmem <= 227 * 1024, "shared memory budget");
 constexpr int kPipeStatSlots = 8;              // per role: cycles the warps spent waiting (debug, see fnerf_debug_pipe_stats)
 
@@ -163,6 +171,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (Rl.rank1) {
+    const float* wa = reinterpret_cast<const float*>(P.packed + kSecBOffset) + kAuxWAlpha + half * 128;
+    for (int n = threadIdx.x; n < 128; n += kPipeThreads) reinterpret_cast<float*>(base_ptr + kPOffWal)[n] = wa[n];
+  }
   if (kind == ROLE_V) {
     // constant B operand of the dZv product (K-major, K = 16): row n = HV unit n, columns (k): 0..2 = bf16(w_c[n]), 3 = 0
     // (the sigma column of the G image), 4..6 = bf16(w_c[n]) again (they meet the low parts of g), 7..9 = the low parts
@@ -201,7 +213,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     spin_until_ge(c + 2, target);
   };
   auto ring_tile = [&](int ring, int64_t i) {
-    return P.ring + ((size_t)(ring * kPipeLanes + lane_g) * kPipeDepth + (size_t)(i % kPipeDepth)) * kTileB;
+    const int d = ring_depth(ring);
+    return P.ring + ((size_t)ring_first_tile(ring) + (size_t)lane_g * d + (size_t)(i % d)) * kTileB;
+  };
+  // job sequence of this CTA: tile i of the lane per job.  The L0 role interleaves two streams: dZ5 of tile i (for
+  // dW5[:, 0:63], the xyz-encoding block of the skip layer) and dZ0 of tile i - kZLag (for dW0), both against the tile's
+  // xyz-encoding image.  Returns 0 = end, 1 = run, 2 = nothing at this position.
+  auto next_job = [&](int64_t it, int64_t& i, bool& s5) -> int {
+    if (kind != ROLE_Z) { i = t0 + it * tstep; s5 = false; return i < n_lane ? 1 : 0; }
+    if (it >= 2 * (n_lane + kZLag)) return 0;
+    s5 = !(it & 1);
+    i = (it >> 1) - (s5 ? 0 : kZLag);
+    return (i >= 0 && i < n_lane) ? 1 : 2;
   };
   const int64_t fstride = (int64_t)kTapeFwdSlots * kImg;
   // pairs a tile consumes, in this order (loader, MMA warp and bias warps walk the same sequence of slots):
@@ -228,17 +251,22 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         bulk_g2s(pair_addr(s), src, bytes, bar_full(s));
         ++pc;
       };
-      for (int64_t i = t0; i < n_lane; i += tstep) {
+      for (int64_t it = 0;; ++it) {
+        int64_t i; bool s5;
+        const int jr = next_job(it, i, s5);
+        if (jr == 0) break;
+        if (jr == 2) continue;
         const int64_t tile = lane_g + i * kPipeLanes;
         const uint8_t* ft = P.fwd_tape + tile * fstride;
         const uint8_t* src = nullptr;
         if (kind != ROLE_V) {
           // both halves of the producing layer have published their two images of tile i
+          const int in_ring = s5 ? kRingZ5 : Rl.in_ring;
           const long long c0 = clock64();
-          wait_ready(Rl.in_ring, i);
+          wait_ready(in_ring, i);
           w0 += clock64() - c0;
           fence_proxy_async_global();
-          src = ring_tile(Rl.in_ring, i);
+          src = ring_tile(in_ring, i);
         }
         if (kind == ROLE_T) {
           load(src, kPairB);
@@ -277,10 +305,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
       };
       if (wt_bytes) mbar_wait(bar_wt, 0);
       int64_t kk = 0;
-      for (int64_t i = t0; i < n_lane; i += tstep, ++kk) {
-        const uint32_t first = kk == 0 ? 0u : 1u;        // accumulate flag of the launch-long wgrad accumulators
+      for (int64_t it = 0;; ++it) {
+        int64_t i; bool s5;
+        const int jr = next_job(it, i, s5);
+        if (jr == 0) break;
+        if (jr == 2) continue;
+        const uint32_t first = (kind == ROLE_Z ? i == 0 : kk == 0) ? 0u : 1u;   // accumulate flag of the launch-long wgrad accumulators
         const uint32_t par = (uint32_t)(kk & 1);
-        const bool last = i + tstep >= n_lane;
+        const bool last = kind == ROLE_Z ? (!s5 && i == n_lane - 1) : (i + tstep >= n_lane);
+        ++kk;
         if (kind == ROLE_T) {
           uint32_t sA, pA, sC, pCc, sB, pB, sE = 0, pE = 0;
           slot_of(sA, pA); slot_of(sC, pCc); slot_of(sB, pB);
@@ -344,11 +377,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           slot_of(sA, pA); slot_of(sB, pB); slot_of(sE, pE);
           mbar_wait_t(bar_full(sA), pA, w0);
           mbar_wait_t(bar_full(sB), pB, w0);
-          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring), 1u);
+          if (lane == 0) red_release_gpu_add(done + (s5 ? flag_idx(kRingZ5) + 4 : flag_idx(Rl.in_ring)), 1u);
           mbar_wait_t(bar_full(sE), pE, w0);
           tc_fence_after();
           if (elect_one()) {
-            const PipeProduct& pr = Rl.prod[0];
+            const PipeProduct& pr = Rl.prod[s5 ? 1 : 0];
             wgrad((uint32_t)pr.tmem_col, pair_addr(sA), pair_addr(sE), pr.ncols, first);
             wgrad((uint32_t)(pr.tmem_col + pr.ncols), pair_addr(sB), pair_addr(sE), pr.ncols, first);
             umma_commit(bar_empty(sA)); umma_commit(bar_empty(sB)); umma_commit(bar_empty(sE));
@@ -422,9 +455,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         for (int jj = 0; jj < 4; ++jj) {
           const int ii = c * 4 + jj;
           float lo = __uint_as_float(v[2 * ii]), hi = __uint_as_float(v[2 * ii + 1]);
-          if (wal != nullptr) {
-            lo = fmaf(gsig, __ldg(wal + 2 * ii), lo);
-            hi = fmaf(gsig, __ldg(wal + 2 * ii + 1), hi);
+          if (wal != nullptr) {                        // shared memory, same address in every lane: broadcast reads
+            lo = fmaf(gsig, wal[2 * ii], lo);
+            hi = fmaf(gsig, wal[2 * ii + 1], hi);
           }
           if (!(mk & (1u << ii))) lo = 0.0f;
           if (!(mk & (1u << (16 + ii)))) hi = 0.0f;
@@ -508,7 +541,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_dg_empty);               // the accumulator may be overwritten by the next tile
         mbar_wait_t(bar_img_empty(j), par ^ 1u, w2);            // the store of the previous tile has read the staging image
-        const float* wal = Rl.rank1 ? aux + kAuxWAlpha + half * 128 + (int)j * 64 : nullptr;
+        const float* wal = Rl.rank1 ? reinterpret_cast<const float*>(base_ptr + kPOffWal) + (int)j * 64 : nullptr;
         emit(v0, mk0, stage_row, 0, gr.w, wal);
         emit(v1, mk1, stage_row, 1, gr.w, wal ? wal + 32 : nullptr);
         fence_proxy_async_smem();
@@ -582,7 +615,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     };
     uint32_t pc = 0;
     int64_t kk = 0;
-    for (int64_t i = t0; i < n_lane; i += tstep, ++kk) {
+    for (int64_t it = 0;; ++it) {
+      int64_t i; bool s5;
+      const int jr = next_job(it, i, s5);
+      if (jr == 0) break;
+      if (jr == 2) continue;
       for (int k = 0; k < n_seq; ++k, ++pc) {
         const uint32_t s = pc % npairs;
         mbar_wait(bar_full(s), (pc / npairs) & 1u);
@@ -590,7 +627,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         if (kind == ROLE_T && k == (half ? 2 : 0)) {
           // images {2 half, 2 half + 1} of dZ (pair A or B): warp sel -> image sel / 2, rows half sel % 2
           colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, b0, b1);
-        } else if (kind == ROLE_Z && k < 2) {
+        } else if (kind == ROLE_Z && k < 2 && !s5) {
           // all four images: pair k, warp sel -> image sel / 2 of the pair, rows half sel % 2
           if (k == 0) colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, b0, b1);
           else colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, c0, c1);
@@ -605,6 +642,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_zv_empty);
       }
+      ++kk;
     }
     if (has_work && Rl.bias != nullptr) {
       if (kind == ROLE_T) {
@@ -645,10 +683,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           publish_upto(kk);
           mbar_wait_t(bar_img_full(j), par, w0);
         }
-        if (i >= kPipeDepth) {                                 // every consumer half has tile i - depth in its shared memory
+        const int depth = ring_depth(Rl.out_ring);
+        if (i >= depth) {                                      // every consumer has tile i - depth in its shared memory
           const long long c0 = clock64();
-          spin_until_ge(done + flag_idx(Rl.out_ring), (uint32_t)(i - kPipeDepth + 1));
-          if (Rl.out_ring != kPipeRings - 1) spin_until_ge(done + flag_idx(Rl.out_ring) + 2, (uint32_t)(i - kPipeDepth + 1));
+          const uint32_t target = (uint32_t)(i - depth + 1);
+          spin_until_ge(done + flag_idx(Rl.out_ring), target);
+          if (Rl.out_ring != kPipeRings - 1) spin_until_ge(done + flag_idx(Rl.out_ring) + 2, target);
+          if (Rl.out_ring == kRingZ5) spin_until_ge(done + flag_idx(Rl.out_ring) + 4, target);
           w1 += clock64() - c0;
         }
         bulk_s2g(ring_tile(Rl.out_ring, i) + (size_t)(2 * half + (int)j) * kImg, base + off_stage + j * kImg, kImg);
@@ -675,7 +716,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
 static unsigned long long* g_pipe_stats = nullptr;     // debug: device buffer [kPipeRoles][kPipeStatSlots], see fnerf_debug_pipe_stats
 
 int64_t mlp_bwd_pipe_workspace_bytes() {
-  return (int64_t)kPipeRings * kPipeLanes * kPipeDepth * kTileB + 2 * (int64_t)kPipeRings * kPipeLanes * 32 * 4 + 1024;
+  return kRingTiles * kTileB + 2 * (int64_t)kPipeRings * kPipeLanes * 32 * 4 + 1024;
 }
 
 // flat_grad += dL/dparams of an UNCONDITIONED network from its forward tape and g_raw[M,4]
@@ -693,7 +734,7 @@ int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape
   P.mask_tape = reinterpret_cast<const uint32_t*>(P.fwd_tape + ntiles * (int64_t)kTapeFwdSlots * kImg);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
   P.ring = w8;
-  P.flags = reinterpret_cast<uint32_t*>(w8 + (int64_t)kPipeRings * kPipeLanes * kPipeDepth * kTileB);
+  P.flags = reinterpret_cast<uint32_t*>(w8 + kRingTiles * kTileB);
   P.flat_grad = flat_grad; P.M = M; P.ntiles = ntiles;
   P.stats = g_pipe_stats;
   auto gw = [&](int l) { return flat_grad + flat_weight_offset(l, cond); };
@@ -741,11 +782,7 @@ int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape
       const int ld = layer == 5 ? in5 : kW;
       R.prod[0] = prod(gw(layer) + (layer == 5 ? kPE : 0) + 128 * h, ld, 1, 128, 2, 128, 0, 128);
       R.nprod = 1;
-      if (layer == 5 && h == 0) {
-        R.e_slot = kTapeSlotPe;
-        R.prod[1] = prod(gw(5), in5, 1, 384, 2, 64, 0, kPE);
-        R.nprod = 2;
-      }
+
     }
   }
   {
@@ -755,7 +792,8 @@ int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape
     R.mask_unit0 = -1; R.rank1 = 0; R.e_slot = kTapeSlotPe; R.p_slot[0] = R.p_slot[1] = -1;
     R.bias = gb(0);
     R.prod[0] = prod(gw(0), kPE, 1, 0, 2, 64, 0, kPE);
-    R.nprod = 1;
+    R.prod[1] = prod(gw(5), in5, 1, 128, 2, 64, 0, kPE);      // dW5[:, 0:63] from the dZ5 stream
+    R.nprod = 2;
   }
   cudaError_t e = cudaMemsetAsync(P.flags, 0, 2 * (size_t)kPipeRings * kPipeLanes * 32 * 4, s);
   if (e != cudaSuccess) return set_error((int)e, "mlp_bwd_pipe memset: %s", cudaGetErrorString(e));
