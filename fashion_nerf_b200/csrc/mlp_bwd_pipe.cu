@@ -32,19 +32,18 @@
 namespace fnerf {
 using namespace ptx;
 
-constexpr int kPipeLanes = 7;
-constexpr int kPipeRoles = 21;                 // V0a V0b V1a V1b F0 F1 L7_0 L7_1 ... L1_0 L1_1 L0
+constexpr int kPipeLanes = 6;
+constexpr int kPipeRoles = 24;                 // V0a V0b V1a V1b F0 F1 L7_0 L7_1 ... L1_0 L1_1 Z0a Z0b Z5a Z5b
 constexpr int kPipeRings = 9;                  // V->F, F->L7, L7->L6, ..., L1->L0
 constexpr int kPipeDepth = 8;                  // tiles per ring (covers the store -> flag -> poll -> load round trip)
-constexpr int kZLag = 12;                      // the L0 role consumes dZ0 of tile i - kZLag right after dZ5 of tile i ...
-constexpr int kPipeDepthLast = 24;             // ... so the last ring (L1 -> L0) holds that many tiles more
+constexpr int kPipeDepthLast = 8;
 constexpr int kRingZ5 = 3;                     // ring L6 -> L5 (dZ5): third consumer = the L0 role (dW5[:, 0:63])
 __host__ __device__ constexpr int ring_depth(int r) { return r == kPipeRings - 1 ? kPipeDepthLast : kPipeDepth; }
 __host__ __device__ constexpr int64_t ring_first_tile(int r) { return (int64_t)r * kPipeLanes * kPipeDepth; }   // rings 0..r-1 are kPipeDepth deep
 constexpr int64_t kRingTiles = ring_first_tile(kPipeRings - 1) + (int64_t)kPipeLanes * kPipeDepthLast;
 constexpr int kPipeThreads = 512;              // warps: 0 loader, 1 MMA, 2..9 epilogue, 10..13 bias sums, 14..15 ring stores
 constexpr uint32_t kImg = 16384, kPairB = 32768, kTileB = 65536;
-constexpr int kMaxPairs = 4;
+constexpr int kMaxPairs = 7;
 // shared memory (role dependent, see the map in the kernel):
 //   trunk: W^T half 64 KB | staging 32 KB | 4 pair slots 128 KB
 //   view:  W^T half 32 KB | staging 32 KB | dZv pair 32 KB | G image 16 KB | W_rgb tile 16 KB | 3 pair slots 96 KB
@@ -52,11 +51,11 @@ constexpr int kMaxPairs = 4;
 constexpr uint32_t kPOffWt = 0;
 constexpr uint32_t kPOffBar = 229376;
 constexpr uint32_t kPNumBars = 2 * kMaxPairs + 14;
-constexpr uint32_t kPOffWal = kPOffBar + 256;      // F roles: w_alpha[half] (128 fp32) for the rank-1 sigma term
+constexpr uint32_t kPOffWal = kPOffBar + 256;      // F roles: w_alpha[half] (128 fp32) for the rank-1 sigma term; L0 role: its job queue
 static_assert(kPNumBars * 8 + 16 <= 256, "barrier block");
 constexpr uint32_t kPipeSmem = kPOffWal + 512 + 1024;
 static_assert(kPipeSmem <= 227 * 1024, "shared memory budget");
-constexpr int kPipeStatSlots = 8;              // per role: cycles the warps spent waiting (debug, see fnerf_debug_pipe_stats)
+constexpr int kPipeStatSlots = 12;             // per role: cycles the warps spent waiting (debug, see fnerf_debug_pipe_stats)
 
 enum { ROLE_V = 0, ROLE_T = 1, ROLE_Z = 2 };
 
@@ -96,8 +95,20 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint64_t ld_acquire_gpu_u64(const void* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// both 32-bit counters packed in one 8-byte word have reached `target`
+__device__ __forceinline__ bool pair_ge(uint64_t v, uint32_t target) {
+  return (int32_t)((uint32_t)v - target) >= 0 && (int32_t)((uint32_t)(v >> 32) - target) >= 0;
+}
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
   const uint32_t off_g = off_zv + kPairB;
   const uint32_t off_wrgb = off_g + kImg;
   const uint32_t off_ring = kind == ROLE_V ? off_wrgb + kImg : (kind == ROLE_Z ? 0u : off_stage + kPairB);
-  const int npairs = kind == ROLE_V ? 3 : 4;
+  const int npairs = kind == ROLE_V ? 3 : (kind == ROLE_Z ? 7 : 4);   // L0 role: all of shared memory is its load ring
   const uint32_t bar0 = base + kPOffBar;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kMaxPairs + s); };
@@ -203,28 +214,29 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
   uint32_t* ready = P.flags;
   uint32_t* done = P.flags + kPipeRings * kPipeLanes * 32;
   auto flag_idx = [&](int ring) { return (ring * kPipeLanes + lane_g) * 32; };
-  // `ready` counters: one per producing CTA of a ring = (half, tile parity for ring 0 whose producers alternate); a
-  // counter counts the images its CTA has published, two per tile
-  auto wait_ready = [&](int ring, int64_t i) {
+  // `ready` counters: one per producing CTA of a ring = (half, tile parity for ring 0 whose producers alternate), word
+  // 2 * parity + half; a counter counts the images its CTA has published, two per tile.  The two halves of a parity sit in
+  // one 8-byte word, so a consumer polls with ONE acquire load (each poll is an L2 round trip on the loader's critical path).
+  auto is_ready = [&](int ring, int64_t i) {
     const int np = ring == 0 ? 2 : 1;
-    const uint32_t* c = ready + flag_idx(ring) + (int)(i % np);
-    const uint32_t target = (uint32_t)(2 * (i / np + 1));
-    spin_until_ge(c, target);
-    spin_until_ge(c + 2, target);
+    return pair_ge(ld_acquire_gpu_u64(ready + flag_idx(ring) + 2 * (int)(i % np)), (uint32_t)(2 * (i / np + 1)));
+  };
+  auto wait_ready = [&](int ring, int64_t i) {
+    if (is_ready(ring, i)) return;
+    const uint64_t tstart = global_timer_ns();
+    while (!is_ready(ring, i)) {
+      __nanosleep(32);
+      if (global_timer_ns() - tstart > 4000000000ull) __trap();
+    }
   };
   auto ring_tile = [&](int ring, int64_t i) {
     const int d = ring_depth(ring);
     return P.ring + ((size_t)ring_first_tile(ring) + (size_t)lane_g * d + (size_t)(i % d)) * kTileB;
   };
-  // job sequence of this CTA: tile i of the lane per job.  The L0 role interleaves two streams: dZ5 of tile i (for
-  // dW5[:, 0:63], the xyz-encoding block of the skip layer) and dZ0 of tile i - kZLag (for dW0), both against the tile's
-  // xyz-encoding image.  Returns 0 = end, 1 = run, 2 = nothing at this position.
+  // job sequence of this CTA: its k-th job is tile t0 + k * tstep of the lane
   auto next_job = [&](int64_t it, int64_t& i, bool& s5) -> int {
-    if (kind != ROLE_Z) { i = t0 + it * tstep; s5 = false; return i < n_lane ? 1 : 0; }
-    if (it >= 2 * (n_lane + kZLag)) return 0;
-    s5 = !(it & 1);
-    i = (it >> 1) - (s5 ? 0 : kZLag);
-    return (i >= 0 && i < n_lane) ? 1 : 2;
+    i = t0 + it * tstep; s5 = false;
+    return i < n_lane ? 1 : 0;
   };
   const int64_t fstride = (int64_t)kTapeFwdSlots * kImg;
   // pairs a tile consumes, in this order (loader, MMA warp and bias warps walk the same sequence of slots):
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
   //   V: C (FEAT half pair)  P0 (HV pair | PED image)  P1 (H7 half pair)
   //   Z: A  B  E
   const int n_seq = kind == ROLE_T ? (Rl.e_slot >= 0 ? 4 : 3) : 3;
-  long long w0 = 0, w1 = 0, w2 = 0;            // debug statistics: cycles spent waiting
+  long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;            // debug statistics: cycles spent waiting
 
   if (warp == 0) {
     // ================================ loader ========================================================
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         const uint8_t* src = nullptr;
         if (kind != ROLE_V) {
           // both halves of the producing layer have published their two images of tile i
-          const int in_ring = s5 ? kRingZ5 : Rl.in_ring;
+          const int in_ring = Rl.in_ring;
           const long long c0 = clock64();
           wait_ready(in_ring, i);
           w0 += clock64() - c0;
@@ -310,9 +322,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         const int jr = next_job(it, i, s5);
         if (jr == 0) break;
         if (jr == 2) continue;
-        const uint32_t first = (kind == ROLE_Z ? i == 0 : kk == 0) ? 0u : 1u;   // accumulate flag of the launch-long wgrad accumulators
+        const uint32_t first = kk == 0 ? 0u : 1u;        // accumulate flag of the launch-long wgrad accumulators
         const uint32_t par = (uint32_t)(kk & 1);
-        const bool last = kind == ROLE_Z ? (!s5 && i == n_lane - 1) : (i + tstep >= n_lane);
+        const bool last = i + tstep >= n_lane;
         ++kk;
         if (kind == ROLE_T) {
           uint32_t sA, pA, sC, pCc, sB, pB, sE = 0, pE = 0;
@@ -342,7 +354,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           __syncwarp();
           mbar_wait_t(bar_full(sB), pB, w0);
           tc_fence_after();
-          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + 2 * half, 1u);    // this half holds tile i in shared memory
+          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + half, 1u);    // this half holds tile i in shared memory
           if (elect_one()) {
             for (int kb = 2; kb < 4; ++kb) {
               const uint64_t a = kdesc(pair_addr(sB) + (uint32_t)(kb & 1) * kImg), b = kdesc(base + kPOffWt + (uint32_t)kb * kImg);
@@ -377,11 +389,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           slot_of(sA, pA); slot_of(sB, pB); slot_of(sE, pE);
           mbar_wait_t(bar_full(sA), pA, w0);
           mbar_wait_t(bar_full(sB), pB, w0);
-          if (lane == 0) red_release_gpu_add(done + (s5 ? flag_idx(kRingZ5) + 4 : flag_idx(Rl.in_ring)), 1u);
+          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + 2 + (int)t0, 1u);
           mbar_wait_t(bar_full(sE), pE, w0);
           tc_fence_after();
           if (elect_one()) {
-            const PipeProduct& pr = Rl.prod[s5 ? 1 : 0];
+            const PipeProduct& pr = Rl.prod[0];
             wgrad((uint32_t)pr.tmem_col, pair_addr(sA), pair_addr(sE), pr.ncols, first);
             wgrad((uint32_t)(pr.tmem_col + pr.ncols), pair_addr(sB), pair_addr(sE), pr.ncols, first);
             umma_commit(bar_empty(sA)); umma_commit(bar_empty(sB)); umma_commit(bar_empty(sE));
@@ -444,7 +456,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     const uint32_t j = (uint32_t)(warp - 2) >> 2;             // output image of the half (64 columns)
     const uint32_t row = q * 32u + (uint32_t)lane;
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
-    const float* aux = reinterpret_cast<const float*>(P.packed + kSecBOffset);
     float gs0 = 0.f, gs1 = 0.f, gs2 = 0.f, gs3 = 0.f;         // V0: sums of g_raw (head bias gradients)
     // accumulator columns -> (+ rank-1 term) -> mask -> bf16 -> one swizzled 64-column image row
     auto emit = [&](const uint32_t (&v)[32], uint32_t mk, uint32_t dst_row, int u, float gsig, const float* wal) {
@@ -627,7 +638,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         if (kind == ROLE_T && k == (half ? 2 : 0)) {
           // images {2 half, 2 half + 1} of dZ (pair A or B): warp sel -> image sel / 2, rows half sel % 2
           colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, b0, b1);
-        } else if (kind == ROLE_Z && k < 2 && !s5) {
+        } else if (kind == ROLE_Z && k < 2 && Rl.bias != nullptr) {
           // all four images: pair k, warp sel -> image sel / 2 of the pair, rows half sel % 2
           if (k == 0) colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, b0, b1);
           else colsum(pair + (uint32_t)(sel >> 1) * kImg, (uint32_t)(sel & 1) * 64u, 64u, c0, c1);
@@ -666,7 +677,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     const uint32_t j = (uint32_t)warp - 14u;
     if (lane == 0 && kind != ROLE_Z && has_work) {
       int64_t published = 0;                                   // in units of this CTA's tiles
-      uint32_t* rdy = ready + flag_idx(Rl.out_ring) + 2 * half + (int)t0;
+      uint32_t* rdy = ready + flag_idx(Rl.out_ring) + 2 * (int)t0 + half;
       auto publish_upto = [&](int64_t n) {                     // tiles [published, n) have completed their stores
         if (n > published) {
           fence_proxy_async_global();
@@ -686,22 +697,37 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         const int depth = ring_depth(Rl.out_ring);
         if (i >= depth) {                                      // every consumer has tile i - depth in its shared memory
           const long long c0 = clock64();
+          // consumers: the two halves of the next layer (words 0, 1; in tile order) and, on the dZ5 / dZ0 rings, the two
+          // alternating Z CTAs (words 2, 3; CTA p counts the tiles of parity p)
           const uint32_t target = (uint32_t)(i - depth + 1);
-          spin_until_ge(done + flag_idx(Rl.out_ring), target);
-          if (Rl.out_ring != kPipeRings - 1) spin_until_ge(done + flag_idx(Rl.out_ring) + 2, target);
-          if (Rl.out_ring == kRingZ5) spin_until_ge(done + flag_idx(Rl.out_ring) + 4, target);
+          if (Rl.out_ring != kPipeRings - 1) {
+            spin_until_ge(done + flag_idx(Rl.out_ring), target);
+            spin_until_ge(done + flag_idx(Rl.out_ring) + 1, target);
+          }
+          if (Rl.out_ring == kRingZ5 || Rl.out_ring == kPipeRings - 1)
+            spin_until_ge(done + flag_idx(Rl.out_ring) + 2 + (int)((i - depth) & 1), (uint32_t)((i - depth) / 2 + 1));
           w1 += clock64() - c0;
         }
         bulk_s2g(ring_tile(Rl.out_ring, i) + (size_t)(2 * half + (int)j) * kImg, base + off_stage + j * kImg, kImg);
         bulk_commit();
+        long long c1 = clock64();
         bulk_wait_read<0>();
+        long long c2 = clock64();
+        w2 += c2 - c1;
         mbar_arrive(bar_img_empty(j));
         bulk_wait_all<1>();                                    // every store but the newest has completed
+        c1 = clock64();
+        w3 += c1 - c2;
         publish_upto(kk);
+        w4 += clock64() - c1;
       }
       bulk_wait_all<0>();
       publish_upto(kk);
-      if (P.stats && j == 0) { atomicAdd(P.stats + role_id * kPipeStatSlots + 7, (unsigned long long)w0); }
+      if (P.stats && j == 0) {
+        atomicAdd(P.stats + role_id * kPipeStatSlots + 7, (unsigned long long)w0); atomicAdd(P.stats + role_id * kPipeStatSlots + 8, (unsigned long long)w1);
+        atomicAdd(P.stats + role_id * kPipeStatSlots + 9, (unsigned long long)w2); atomicAdd(P.stats + role_id * kPipeStatSlots + 10, (unsigned long long)w3);
+        atomicAdd(P.stats + role_id * kPipeStatSlots + 11, (unsigned long long)w4);
+      }
     }
   }
 
@@ -785,15 +811,17 @@ int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape
 
     }
   }
-  {
+  // Z0a Z0b Z5a Z5b: the two products against the xyz encoding, dW0 += dZ0^T . PE (+ bias 0) and dW5[:, 0:63] += dZ5^T . PE,
+  // each by two CTAs that alternate over the lane's tiles (a tile costs 80 KB of loads for ~600 cycles of MMAs: latency-bound)
+  for (int zp = 0; zp < 4; ++zp) {
+    const bool z5 = zp >= 2;
     PipeRole& R = P.roles[r++];
-    R.t0 = 0; R.tstep = 1;
-    R.kind = ROLE_Z; R.half = 0; R.in_ring = 8; R.out_ring = -1; R.wt_chunk0 = 0; R.wt_nchunks = 0; R.x_slot = 0;
+    R.t0 = zp & 1; R.tstep = 2;
+    R.kind = ROLE_Z; R.half = 0; R.in_ring = z5 ? kRingZ5 : kPipeRings - 1; R.out_ring = -1; R.wt_chunk0 = 0; R.wt_nchunks = 0; R.x_slot = 0;
     R.mask_unit0 = -1; R.rank1 = 0; R.e_slot = kTapeSlotPe; R.p_slot[0] = R.p_slot[1] = -1;
-    R.bias = gb(0);
-    R.prod[0] = prod(gw(0), kPE, 1, 0, 2, 64, 0, kPE);
-    R.prod[1] = prod(gw(5), in5, 1, 128, 2, 64, 0, kPE);      // dW5[:, 0:63] from the dZ5 stream
-    R.nprod = 2;
+    R.bias = z5 ? nullptr : gb(0);
+    R.prod[0] = z5 ? prod(gw(5), in5, 1, 0, 2, 64, 0, kPE) : prod(gw(0), kPE, 1, 0, 2, 64, 0, kPE);
+    R.nprod = 1;
   }
   cudaError_t e = cudaMemsetAsync(P.flags, 0, 2 * (size_t)kPipeRings * kPipeLanes * 32 * 4, s);
   if (e != cudaSuccess) return set_error((int)e, "mlp_bwd_pipe memset: %s", cudaGetErrorString(e));

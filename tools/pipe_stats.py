@@ -24,10 +24,10 @@ tr.step(o, d, tgt, 2.0, 6.0, 64, 128, u_strat=u_s, u_fine=u_f)
 e1.record()
 torch.cuda.synchronize()
 lib.fnerf_debug_pipe_stats(None)
-print(f"step {e0.elapsed_time(e1):.3f} ms (coarse + fine backward accumulated below; 7 CTAs per role; Mcycles)")
-names = ["V0a", "V0b", "V1a", "V1b", "F0", "F1"] + [f"L{l}_{h}" for l in range(7, 0, -1) for h in (0, 1)] + ["L0"]
-hdr = ["ld:ring", "ld:slot", "mma:opnd", "mma:acc", "epi:acc", "epi:buf", "epi:stage", "st:img"]
+print(f"step {e0.elapsed_time(e1):.3f} ms (coarse + fine backward accumulated below; 6 CTAs per role; Mcycles)")
+names = ["V0a", "V0b", "V1a", "V1b", "F0", "F1"] + [f"L{l}_{h}" for l in range(7, 0, -1) for h in (0, 1)] + ["Z0a", "Z0b", "Z5a", "Z5b"]
+hdr = ["ld:ring", "ld:slot", "mma:opnd", "mma:acc", "epi:acc", "epi:buf", "epi:stage", "st:img", "st:done", "st:read", "st:compl", "st:publ"]
 print(f"{'role':6s}" + "".join(f"{h:>10s}" for h in hdr))
-s = stats.view(-1, 8).cpu()
+s = stats.view(-1, 12).cpu()
 for r, nm in enumerate(names):
-    print(f"{nm:6s}" + "".join(f"{s[r, k].item() / 7e6:10.2f}" for k in range(8)))
+    print(f"{nm:6s}" + "".join(f"{s[r, k].item() / 6e6:10.2f}" for k in range(12)))
