@@ -95,15 +95,14 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ uint64_t ld_acquire_gpu_u64(const void* p) {
-  uint64_t v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+// Polls use RELAXED gpu-scope loads: an acquire load drags a CCTL.IVALL (whole-L1 invalidate) along on every poll, and
+// what a successful poll guards is read by bulk TMA from L2, never through L1.  One 16-byte load fetches all counters.
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-// both 32-bit counters packed in one 8-byte word have reached `target`
-__device__ __forceinline__ bool pair_ge(uint64_t v, uint32_t target) {
-  return (int32_t)((uint32_t)v - target) >= 0 && (int32_t)((uint32_t)(v >> 32) - target) >= 0;
-}
+__device__ __forceinline__ bool cnt_ge(uint32_t v, uint32_t target) { return (int32_t)(v - target) >= 0; }
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -214,12 +213,22 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
   uint32_t* ready = P.flags;
   uint32_t* done = P.flags + kPipeRings * kPipeLanes * 32;
   auto flag_idx = [&](int ring) { return (ring * kPipeLanes + lane_g) * 32; };
-  // `ready` counters: one per producing CTA of a ring = (half, tile parity for ring 0 whose producers alternate), word
-  // 2 * parity + half; a counter counts the images its CTA has published, two per tile.  The two halves of a parity sit in
-  // one 8-byte word, so a consumer polls with ONE acquire load (each poll is an L2 round trip on the loader's critical path).
+  // `ready` counters: one per store thread of a ring = (tile parity for ring 0 whose producers alternate, half, image),
+  // word 4 * parity + 2 * half + image, counting the tiles that thread has published IN ORDER.  The four counters of a
+  // parity sit in one 16-byte word: a consumer polls with ONE load (each poll is an L2 round trip on the loader's critical
+  // path) and remembers what it saw, so a producer that runs ahead is not polled again.
+  uint32_t seen_ready[2] = {0u, 0u};
   auto is_ready = [&](int ring, int64_t i) {
-    const int np = ring == 0 ? 2 : 1;
-    return pair_ge(ld_acquire_gpu_u64(ready + flag_idx(ring) + 2 * (int)(i % np)), (uint32_t)(2 * (i / np + 1)));
+    const int np = ring == 0 ? 2 : 1, par = (int)(i % np);
+    const uint32_t target = (uint32_t)(i / np + 1);
+    if (cnt_ge(seen_ready[par], target)) return true;
+    const uint4 v = ld_relaxed_gpu_v4(ready + flag_idx(ring) + 4 * par);
+    uint32_t m = v.x;
+    if (!cnt_ge(v.y, m)) m = v.y;
+    if (!cnt_ge(v.z, m)) m = v.z;
+    if (!cnt_ge(v.w, m)) m = v.w;
+    seen_ready[par] = m;                       // the slowest of the four publishers
+    return cnt_ge(m, target);
   };
   auto wait_ready = [&](int ring, int64_t i) {
     if (is_ready(ring, i)) return;
@@ -316,6 +325,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           umma_bf16(tm + dcol, a0 + (uint64_t)(ks * 128), b0 + (uint64_t)(ks * 128), idesc, (ks == 0) ? first : 1u);
       };
       if (wt_bytes) mbar_wait(bar_wt, 0);
+      constexpr uint32_t idesc_wg = pipe_idesc_mn(128, 128);
+      const uint64_t kd_ring = kdesc(base + off_ring), md_ring = mndesc(base + off_ring), kd_w = kdesc(base + kPOffWt);
       int64_t kk = 0;
       for (int64_t it = 0;; ++it) {
         int64_t i; bool s5;
@@ -327,58 +338,48 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         const bool last = i + tstep >= n_lane;
         ++kk;
         if (kind == ROLE_T) {
-          uint32_t sA, pA, sC, pCc, sB, pB, sE = 0, pE = 0;
+          uint32_t sA, pA, sC, pCc, sB, pB;
           slot_of(sA, pA); slot_of(sC, pCc); slot_of(sB, pB);
-          if (Rl.e_slot >= 0) slot_of(sE, pE);
-          const PipeProduct& pr = Rl.prod[0];
           // dgrad over K-blocks 0,1 | wgrad M-block 0 | dgrad over K-blocks 2,3 | wgrad M-block 1: pair A is released at
-          // half time, so the loader's prefetch distance (4 pair slots = 1 1/3 tiles) covers the L2 latency
+          // half time, so the loader's prefetch distance (4 pair slots = 1 1/3 tiles) covers the L2 latency.  All 32 MMAs
+          // are N = 128 (64 tensor-pipe cycles each): the issuing thread must not spend more than that per MMA, so every
+          // descriptor below is one 64-bit add on a base computed before the tile loop and every loop is unrolled.
+          const uint64_t aA = kd_ring + (uint64_t)(sA * (kPairB >> 4)), aB = kd_ring + (uint64_t)(sB * (kPairB >> 4));
+          const uint64_t mA = md_ring + (uint64_t)(sA * (kPairB >> 4)), mB = md_ring + (uint64_t)(sB * (kPairB >> 4));
+          const uint64_t mC = md_ring + (uint64_t)(sC * (kPairB >> 4));
           mbar_wait_t(bar_dg_empty, par ^ 1u, w1);
           mbar_wait_t(bar_full(sA), pA, w0);
           tc_fence_after();
           if (elect_one()) {
-            for (int kb = 0; kb < 2; ++kb) {
-              const uint64_t a = kdesc(pair_addr(sA) + (uint32_t)kb * kImg), b = kdesc(base + kPOffWt + (uint32_t)kb * kImg);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(tm, a + (uint64_t)(2 * ks), b + (uint64_t)(2 * ks), idesc_dg, (kb | ks) ? 1u : 0u);
-            }
+                umma_bf16(tm, aA + (uint64_t)(kb * (kImg >> 4) + 2 * ks), kd_w + (uint64_t)(kb * (kImg >> 4) + 2 * ks), idesc_dg, (kb | ks) ? 1u : 0u);
           }
           __syncwarp();
           mbar_wait_t(bar_full(sC), pCc, w0);
           tc_fence_after();
           if (elect_one()) {
-            wgrad((uint32_t)pr.tmem_col, pair_addr(sA), pair_addr(sC), pr.ncols, first);
-            if (Rl.e_slot < 0) umma_commit(bar_empty(sA));
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16(tm + 128u, mA + (uint64_t)(ks * 128), mC + (uint64_t)(ks * 128), idesc_wg, ks == 0 ? first : 1u);
+            umma_commit(bar_empty(sA));
           }
           __syncwarp();
           mbar_wait_t(bar_full(sB), pB, w0);
           tc_fence_after();
-          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + half, 1u);    // this half holds tile i in shared memory
+          if (lane == 0) red_relaxed_gpu_add(done + flag_idx(Rl.in_ring) + half, 1u);    // this half holds tile i in shared memory
           if (elect_one()) {
-            for (int kb = 2; kb < 4; ++kb) {
-              const uint64_t a = kdesc(pair_addr(sB) + (uint32_t)(kb & 1) * kImg), b = kdesc(base + kPOffWt + (uint32_t)kb * kImg);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(tm, a + (uint64_t)(2 * ks), b + (uint64_t)(2 * ks), idesc_dg, 1u);
-            }
+                umma_bf16(tm, aB + (uint64_t)(kb * (kImg >> 4) + 2 * ks), kd_w + (uint64_t)((kb + 2) * (kImg >> 4) + 2 * ks), idesc_dg, 1u);
             umma_commit(bar_dg_full);
-            wgrad((uint32_t)(pr.tmem_col + pr.ncols), pair_addr(sB), pair_addr(sC), pr.ncols, first);
-          }
-          __syncwarp();
-          if (Rl.e_slot >= 0) {                            // L5_0: dW5[:, 0:63] += dZ5^T . PE
-            mbar_wait_t(bar_full(sE), pE, w0);
-            tc_fence_after();
-            if (elect_one()) {
-              const PipeProduct& pe = Rl.prod[1];
-              wgrad((uint32_t)pe.tmem_col, pair_addr(sA), pair_addr(sE), pe.ncols, first);
-              wgrad((uint32_t)(pe.tmem_col + pe.ncols), pair_addr(sB), pair_addr(sE), pe.ncols, first);
-              umma_commit(bar_empty(sA));
-              umma_commit(bar_empty(sE));
-            }
-            __syncwarp();
-          }
-          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16(tm + 256u, mB + (uint64_t)(ks * 128), mC + (uint64_t)(ks * 128), idesc_wg, ks == 0 ? first : 1u);
             umma_commit(bar_empty(sC));
             umma_commit(bar_empty(sB));
             if (last) umma_commit(bar_done);
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           slot_of(sA, pA); slot_of(sB, pB); slot_of(sE, pE);
           mbar_wait_t(bar_full(sA), pA, w0);
           mbar_wait_t(bar_full(sB), pB, w0);
-          if (lane == 0) red_release_gpu_add(done + flag_idx(Rl.in_ring) + 2 + (int)t0, 1u);
+          if (lane == 0) red_relaxed_gpu_add(done + flag_idx(Rl.in_ring) + 2 + (int)t0, 1u);
           mbar_wait_t(bar_full(sE), pE, w0);
           tc_fence_after();
           if (elect_one()) {
@@ -677,49 +678,62 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
     const uint32_t j = (uint32_t)warp - 14u;
     if (lane == 0 && kind != ROLE_Z && has_work) {
       int64_t published = 0;                                   // in units of this CTA's tiles
-      uint32_t* rdy = ready + flag_idx(Rl.out_ring) + 2 * (int)t0 + half;
+      uint32_t* rdy = ready + flag_idx(Rl.out_ring) + 4 * (int)t0 + 2 * half + (int)j;
+      // credits: the `done` counters of the ring's consumers (words 0, 1: the halves of the next layer, in tile order;
+      // words 2, 3: on the dZ5 / dZ0 rings the alternating Z CTAs, CTA p counting the tiles of parity p), cached
+      uint4 seen_done = make_uint4(0u, 0u, 0u, 0u);
+      const bool has_halves = Rl.out_ring != kPipeRings - 1, has_z = Rl.out_ring == kRingZ5 || Rl.out_ring == kPipeRings - 1;
+      auto has_credit = [&](int64_t old_tile) {               // every consumer has `old_tile` in its shared memory
+        const uint32_t th = (uint32_t)(old_tile + 1), tz = (uint32_t)(old_tile / 2 + 1);
+        const uint32_t zc = (old_tile & 1) ? seen_done.w : seen_done.z;
+        return (!has_halves || (cnt_ge(seen_done.x, th) && cnt_ge(seen_done.y, th))) && (!has_z || cnt_ge(zc, tz));
+      };
       auto publish_upto = [&](int64_t n) {                     // tiles [published, n) have completed their stores
         if (n > published) {
+          // the stores of these tiles have completed (wait_group); the proxy fence orders the async-proxy writes before
+          // this thread's release, which publishes them at gpu scope
           fence_proxy_async_global();
-          __threadfence();
+#ifdef FNERF_PIPE_RELEASE
           red_release_gpu_add(rdy, (uint32_t)(n - published));
+#else
+          red_relaxed_gpu_add(rdy, (uint32_t)(n - published));
+#endif
           published = n;
         }
       };
       int64_t kk = 0;
       for (int64_t i = t0; i < n_lane; i += tstep, ++kk) {
         const uint32_t par = (uint32_t)(kk & 1);
-        if (!mbar_test_wait(bar_img_full(j), par)) {           // nothing to store yet: drain and publish what is in flight
+        // Publish the previous tile BEFORE the next store is issued: the release fence of the publication waits for every
+        // memory operation this thread has in flight, a freshly issued 16 KB store included (that cost 1650 cycles per
+        // tile).  Normally this thread is early and the wait for the store's completion falls into its idle time.
+        {
+          long long c1 = clock64();
           bulk_wait_all<0>();
+          long long c2 = clock64();
+          w3 += c2 - c1;
           publish_upto(kk);
+          w4 += clock64() - c2;
           mbar_wait_t(bar_img_full(j), par, w0);
         }
         const int depth = ring_depth(Rl.out_ring);
-        if (i >= depth) {                                      // every consumer has tile i - depth in its shared memory
+        if (i >= depth && !has_credit(i - depth)) {            // the ring slot still holds a tile some consumer has not loaded
           const long long c0 = clock64();
-          // consumers: the two halves of the next layer (words 0, 1; in tile order) and, on the dZ5 / dZ0 rings, the two
-          // alternating Z CTAs (words 2, 3; CTA p counts the tiles of parity p)
-          const uint32_t target = (uint32_t)(i - depth + 1);
-          if (Rl.out_ring != kPipeRings - 1) {
-            spin_until_ge(done + flag_idx(Rl.out_ring), target);
-            spin_until_ge(done + flag_idx(Rl.out_ring) + 1, target);
+          const uint64_t tstart = global_timer_ns();
+          for (;;) {
+            seen_done = ld_relaxed_gpu_v4(done + flag_idx(Rl.out_ring));
+            if (has_credit(i - depth)) break;
+            __nanosleep(32);
+            if (global_timer_ns() - tstart > 4000000000ull) __trap();
           }
-          if (Rl.out_ring == kRingZ5 || Rl.out_ring == kPipeRings - 1)
-            spin_until_ge(done + flag_idx(Rl.out_ring) + 2 + (int)((i - depth) & 1), (uint32_t)((i - depth) / 2 + 1));
           w1 += clock64() - c0;
         }
         bulk_s2g(ring_tile(Rl.out_ring, i) + (size_t)(2 * half + (int)j) * kImg, base + off_stage + j * kImg, kImg);
         bulk_commit();
-        long long c1 = clock64();
+        const long long c1 = clock64();
         bulk_wait_read<0>();
-        long long c2 = clock64();
-        w2 += c2 - c1;
+        w2 += clock64() - c1;
         mbar_arrive(bar_img_empty(j));
-        bulk_wait_all<1>();                                    // every store but the newest has completed
-        c1 = clock64();
-        w3 += c1 - c2;
-        publish_upto(kk);
-        w4 += clock64() - c1;
       }
       bulk_wait_all<0>();
       publish_upto(kk);
