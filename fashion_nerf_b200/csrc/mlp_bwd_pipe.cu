@@ -35,8 +35,11 @@ using namespace ptx;
 constexpr int kPipeLanes = 6;
 constexpr int kPipeRoles = 24;                 // V0a V0b V1a V1b F0 F1 L7_0 L7_1 ... L1_0 L1_1 Z0a Z0b Z5a Z5b
 constexpr int kPipeRings = 9;                  // V->F, F->L7, L7->L6, ..., L1->L0
-constexpr int kPipeDepth = 8;                  // tiles per ring (covers the store -> flag -> poll -> load round trip)
-constexpr int kPipeDepthLast = 8;
+#ifndef FNERF_PIPE_DEPTH
+#define FNERF_PIPE_DEPTH 8
+#endif
+constexpr int kPipeDepth = FNERF_PIPE_DEPTH;   // tiles per ring (covers the store -> flag -> poll -> load round trip)
+constexpr int kPipeDepthLast = FNERF_PIPE_DEPTH;
 constexpr int kRingZ5 = 3;                     // ring L6 -> L5 (dZ5): third consumer = the L0 role (dW5[:, 0:63])
 __host__ __device__ constexpr int ring_depth(int r) { return r == kPipeRings - 1 ? kPipeDepthLast : kPipeDepth; }
 __host__ __device__ constexpr int64_t ring_first_tile(int r) { return (int64_t)r * kPipeLanes * kPipeDepth; }   // rings 0..r-1 are kPipeDepth deep
@@ -50,9 +53,9 @@ constexpr int kMaxPairs = 7;
 //   L0:    4 pair slots
 constexpr uint32_t kPOffWt = 0;
 constexpr uint32_t kPOffBar = 229376;
-constexpr uint32_t kPNumBars = 2 * kMaxPairs + 14;
+constexpr uint32_t kPNumBars = 2 * kMaxPairs + 16;
 constexpr uint32_t kPOffWal = kPOffBar + 256;      // F roles: w_alpha[half] (128 fp32) for the rank-1 sigma term; L0 role: its job queue
-static_assert(kPNumBars * 8 + 16 <= 256, "barrier block");
+static_assert(kPNumBars * 8 + 16 <= 256, "barrier block");   // 30 barriers + the TMEM slot
 constexpr uint32_t kPipeSmem = kPOffWal + 512 + 1024;
 static_assert(kPipeSmem <= 227 * 1024, "shared memory budget");
 constexpr int kPipeStatSlots = 12;             // per role: cycles the warps spent waiting (debug, see fnerf_debug_pipe_stats)
@@ -90,11 +93,6 @@ struct PipeParams {
   int64_t M, ntiles;
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // Polls use RELAXED gpu-scope loads: an acquire load drags a CCTL.IVALL (whole-L1 invalidate) along on every poll, and
 // what a successful poll guards is read by bulk TMA from L2, never through L1.  One 16-byte load fetches all counters.
 __device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint32_t* p) {
@@ -114,16 +112,8 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// bounded spin on a monotone counter written by another CTA of this launch; a peer that never arrives (a bug, or CTAs that
-// are not co-resident) aborts the launch after 4 s instead of hanging the GPU
-__device__ __forceinline__ void spin_until_ge(const uint32_t* p, uint32_t target) {
-  if ((int32_t)(ld_acquire_gpu(p) - target) >= 0) return;
-  const uint64_t t0 = global_timer_ns();
-  while ((int32_t)(ld_acquire_gpu(p) - target) < 0) {
-    __nanosleep(32);
-    if (global_timer_ns() - t0 > 4000000000ull) __trap();
-  }
-}
+// Every spin on a counter written by another CTA of this launch is bounded: a peer that never arrives (a bug, or CTAs
+// that are not co-resident) aborts the launch with a trap after 4 s instead of hanging the GPU.
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __host__ __device__ constexpr uint32_t pipe_idesc_mn(int M, int N) {   // A and B MN-major
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -167,12 +157,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
   const uint32_t bar_zacc_full = bx + 64u;
   auto bar_img_full = [&](uint32_t j) { return bx + 72u + 8u * j; };
   auto bar_img_empty = [&](uint32_t j) { return bx + 88u + 8u * j; };
+  // trunk roles keep TWO dgrad accumulators (TMEM columns 0 and 384, tile parity) so the next tile's first MMAs need not
+  // wait for this tile's epilogue to have drained the accumulator; buffer 1 has its own barrier pair
+  const uint32_t bar_dg_full1 = bx + 104u, bar_dg_empty1 = bx + 112u;
   const uint32_t tmem_slot = bar0 + 8u * kPNumBars;
   auto pair_addr = [&](int s) { return base + off_ring + (uint32_t)s * kPairB; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxPairs; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1 + 4); }   // MMA commit + 4 bias warps
     mbar_init(bar_dg_full, 1);  mbar_init(bar_dg_empty, 8);
+    mbar_init(bar_dg_full1, 1); mbar_init(bar_dg_empty1, 8);
     mbar_init(bar_zv_full, 8);  mbar_init(bar_zv_empty, 1 + 4);
     mbar_init(bar_g_full, 8);   mbar_init(bar_g_empty, 1);
     mbar_init(bar_done, 1);     mbar_init(bar_wt, 1);
@@ -347,7 +341,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           const uint64_t aA = kd_ring + (uint64_t)(sA * (kPairB >> 4)), aB = kd_ring + (uint64_t)(sB * (kPairB >> 4));
           const uint64_t mA = md_ring + (uint64_t)(sA * (kPairB >> 4)), mB = md_ring + (uint64_t)(sB * (kPairB >> 4));
           const uint64_t mC = md_ring + (uint64_t)(sC * (kPairB >> 4));
-          mbar_wait_t(bar_dg_empty, par ^ 1u, w1);
+          const uint32_t dbuf = (uint32_t)((kk - 1) & 1), dpar = (uint32_t)(((kk - 1) >> 1) & 1);   // kk was incremented above
+          const uint32_t tmd = tm + dbuf * 384u;
+          mbar_wait_t(dbuf ? bar_dg_empty1 : bar_dg_empty, dpar ^ 1u, w1);
           mbar_wait_t(bar_full(sA), pA, w0);
           tc_fence_after();
           if (elect_one()) {
@@ -355,7 +351,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
             for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(tm, aA + (uint64_t)(kb * (kImg >> 4) + 2 * ks), kd_w + (uint64_t)(kb * (kImg >> 4) + 2 * ks), idesc_dg, (kb | ks) ? 1u : 0u);
+                umma_bf16(tmd, aA + (uint64_t)(kb * (kImg >> 4) + 2 * ks), kd_w + (uint64_t)(kb * (kImg >> 4) + 2 * ks), idesc_dg, (kb | ks) ? 1u : 0u);
           }
           __syncwarp();
           mbar_wait_t(bar_full(sC), pCc, w0);
@@ -375,8 +371,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
             for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(tm, aB + (uint64_t)(kb * (kImg >> 4) + 2 * ks), kd_w + (uint64_t)((kb + 2) * (kImg >> 4) + 2 * ks), idesc_dg, 1u);
-            umma_commit(bar_dg_full);
+                umma_bf16(tmd, aB + (uint64_t)(kb * (kImg >> 4) + 2 * ks), kd_w + (uint64_t)((kb + 2) * (kImg >> 4) + 2 * ks), idesc_dg, 1u);
+            umma_commit(dbuf ? bar_dg_full1 : bar_dg_full);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
               umma_bf16(tm + 256u, mB + (uint64_t)(ks * 128), mC + (uint64_t)(ks * 128), idesc_wg, ks == 0 ? first : 1u);
@@ -544,14 +540,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
         }
         // ---- dgrad epilogue: accumulator -> (+ rank-1 sigma term) -> ReLU mask -> bf16 -> staging image j -----
         const uint32_t mk0 = cur.mk0, mk1 = cur.mk1;
-        mbar_wait_t(bar_dg_full, par, w0);
+        const uint32_t dbuf = kind == ROLE_T ? (uint32_t)(kk & 1) : 0u;
+        const uint32_t dpar = kind == ROLE_T ? (uint32_t)((kk >> 1) & 1) : par;
+        mbar_wait_t(dbuf ? bar_dg_full1 : bar_dg_full, dpar, w0);
         tc_fence_after();
-        tmem_ld32(tmem_row + j * 64u, v0);
-        tmem_ld32(tmem_row + j * 64u + 32u, v1);
+        tmem_ld32(tmem_row + dbuf * 384u + j * 64u, v0);
+        tmem_ld32(tmem_row + dbuf * 384u + j * 64u + 32u, v1);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dg_empty);               // the accumulator may be overwritten by the next tile
+        if (lane == 0) mbar_arrive(dbuf ? bar_dg_empty1 : bar_dg_empty);   // this accumulator may be overwritten again
         mbar_wait_t(bar_img_empty(j), par ^ 1u, w2);            // the store of the previous tile has read the staging image
         const float* wal = Rl.rank1 ? reinterpret_cast<const float*>(base_ptr + kPOffWal) + (int)j * 64 : nullptr;
         emit(v0, mk0, stage_row, 0, gr.w, wal);
@@ -693,10 +691,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
           // the stores of these tiles have completed (wait_group); the proxy fence orders the async-proxy writes before
           // this thread's release, which publishes them at gpu scope
           fence_proxy_async_global();
-#ifdef FNERF_PIPE_RELEASE
-          red_release_gpu_add(rdy, (uint32_t)(n - published));
-#else
+#ifdef FNERF_PIPE_RELAXED_PUBLISH              // experiment: ~1500 cycles cheaper per tile, but the publication then leans on the proxy fence alone
           red_relaxed_gpu_add(rdy, (uint32_t)(n - published));
+#else
+          red_release_gpu_add(rdy, (uint32_t)(n - published));
 #endif
           published = n;
         }
@@ -754,6 +752,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_mlp_bwd_pipe(const __grid_c
 }
 
 static unsigned long long* g_pipe_stats = nullptr;     // debug: device buffer [kPipeRoles][kPipeStatSlots], see fnerf_debug_pipe_stats
+
+// the pipeline needs every one of its CTAs resident at the same time, one per SM
+bool mlp_bwd_pipe_supported() { return num_sms() >= kPipeRoles * kPipeLanes; }
 
 int64_t mlp_bwd_pipe_workspace_bytes() {
   return kRingTiles * kTileB + 2 * (int64_t)kPipeRings * kPipeLanes * 32 * 4 + 1024;

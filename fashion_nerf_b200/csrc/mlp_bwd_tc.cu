@@ -228,6 +228,7 @@ int64_t mlp_tape_bytes(int64_t M) {
   return ntiles * ((int64_t)kTapeFwdSlots * 16384 + kMaskTileBytes);
 }
 int64_t mlp_bwd_pipe_workspace_bytes();
+bool mlp_bwd_pipe_supported();
 int launch_mlp_bwd_pipe(const void* packed, const float* g_raw, const void* tape, float* flat_grad, void* ws, int64_t M, cudaStream_t s);
 
 // Which backward runs from a forward tape: the layer-pipelined fused dgrad + wgrad kernel (mlp_bwd_pipe.cu) for
@@ -237,7 +238,7 @@ static bool use_bwd_pipe(int cond) {
   static std::once_flag flag;
   static int enabled = 1;
   std::call_once(flag, [] { const char* e = getenv("FNERF_BWD_PIPE"); if (e) enabled = atoi(e) != 0; });
-  return enabled && !cond;
+  return enabled && !cond && mlp_bwd_pipe_supported();
 }
 
 // backward tape + (conditioned networks) the per-sample garment codes as 4 K-block images per tile; or the pipeline's
