@@ -411,6 +411,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-render", action="store_true", help="skip the train / strong / stages / fp32 sections")
+    ap.add_argument("--fuse", default="auto", choices=["auto", "on", "off"],
+                    help="compositing fused into the network-query kernel (auto = the library default: on for bf16 inference)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -435,10 +437,13 @@ def main():
                for k, s in (("rgb", (R, 3)), ("disp", (R,)), ("acc", (R,)), ("depth", (R,)))}
     dev_gen = torch.Generator(device=dev).manual_seed(1000 + rank)
 
+    fuse = {"auto": None, "on": True, "off": False}[args.fuse]
+    fused = args.precision == "bf16" and fuse is not False
+
     def step_resident():
         with torch.no_grad():
             return F.render_rays(model, o_d, d_d, NEAR, FAR, N_C, N_F, u_strat=u_s, u_fine=u_f,
-                                 precision=args.precision)
+                                 precision=args.precision, fuse_composite=fuse)
 
     def step_e2e():
         with torch.no_grad():
@@ -446,7 +451,8 @@ def main():
             d = d_pin.to(dev, non_blocking=True)
             us = torch.rand(R, N_C, device=dev, generator=dev_gen)          # the caller's jitter, drawn on the device each frame
             uf = torch.rand(R, N_F, device=dev, generator=dev_gen)
-            out = F.render_rays(model, o, d, NEAR, FAR, N_C, N_F, u_strat=us, u_fine=uf, precision=args.precision)
+            out = F.render_rays(model, o, d, NEAR, FAR, N_C, N_F, u_strat=us, u_fine=uf, precision=args.precision,
+                                fuse_composite=fuse)
             for k, buf in out_pin.items():
                 buf.copy_(out[k], non_blocking=True)
         return out
@@ -512,9 +518,11 @@ def main():
         roofline = {"bound": "tensor", "kernel": "k_mlp_tc (fine pass, 192 samples/ray)" if use_bf16 else "k_mlp_fp32",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "peak_kind": f"sustained, {peaks['source']}",
-                    "traffic": NCU_FINE_LAUNCH_DRAM_BYTES if (use_bf16 and R == 640000) else None,
+                    "traffic": NCU_FINE_LAUNCH_DRAM_BYTES if (use_bf16 and R == 640000 and not fused) else None,
                     "traffic_source": NCU_TRAFFIC_SOURCE,
-                    "algorithmic_hbm_bytes": R * (N_C + N_F) * 20,
+                    # z read (4 B/sample) + raw written (16 B/sample) -- or, with compositing fused in, the four maps
+                    "algorithmic_hbm_bytes": R * (N_C + N_F) * 4 + (R * 28 if fused else R * (N_C + N_F) * 16),
+                    "composite_fused": fused,
                     "launch_ms": fine_ms, "coarse_launch_ms": coarse_ms,
                     "kernel_share_of_step": (fine_ms + coarse_ms) / ms_step,
                     "step_tensor_frac": R * FLOP_PER_RAY / (ms_step * 1e-3) / 1e12 / peak}

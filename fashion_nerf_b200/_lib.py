@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FNERF_LIB") or os.path.join(HERE, "libfnerf.so")   # FNERF_LIB: A/B builds (tools/)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 
@@ -41,6 +41,7 @@ class RenderArgs(ctypes.Structure):
         ("ev_fine_start", c_void_p), ("ev_fine_stop", c_void_p),
         ("tape_coarse", c_void_p), ("tape_coarse_bytes", c_int64),
         ("tape_fine", c_void_p), ("tape_fine_bytes", c_int64),
+        ("fuse_composite", c_int),
     ]
 
 
@@ -61,6 +62,10 @@ SIGNATURES = {
     "fnerf_cond_project": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "fnerf_mlp_fwd": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int64, c_void_p, c_int64, c_int64, c_void_p]),
+    "fnerf_mlp_fwd_composite_supported": (c_int, [c_int64]),
+    "fnerf_mlp_fwd_composite": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int64, c_int64, c_int, c_void_p]),
     "fnerf_mlp_bwd_workspace_bytes": (c_int64, [c_int, c_int, c_int64, c_int64]),
     "fnerf_mlp_bwd": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),

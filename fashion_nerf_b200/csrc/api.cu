@@ -193,6 +193,24 @@ int fnerf_multimem_allreduce(float* multicast_ptr, int rank, int world, int64_t 
   return launch_multimem_allreduce(multicast_ptr, rank, world, n, (cudaStream_t)stream);
 }
 
+int fnerf_mlp_fwd_composite_supported(int64_t S) { return mlp_tc_composite_group(S) > 0 ? 1 : 0; }
+
+int fnerf_mlp_fwd_composite(const void* packed, int cond, const float* rays_o, const float* rays_d, const float* viewdirs,
+                            const float* dnorm, const float* z, const float* cond_proj, const int32_t* cond_index, int64_t C,
+                            const float* raw_noise, float* raw, float* rgb, float* depth, float* acc, float* disp, float* weights,
+                            int64_t R, int64_t S, int white_bkgd, fnerf_stream_t stream) {
+  // `raw` is nullable here: validate with a stand-in for the output pointer
+  int rc = validate_mlp("mlp_fwd_composite", FNERF_PRECISION_BF16, packed, cond, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C,
+                        raw ? raw : reinterpret_cast<const float*>(packed), R, S);
+  if (rc != 0 || R == 0) return rc;
+  FN_REQUIRE(dnorm && rgb && depth && acc && disp, FNERF_ERR_NULL, "mlp_fwd_composite: null pointer");
+  FN_REQUIRE(mlp_tc_composite_group(S) > 0, FNERF_ERR_SIZE, "mlp_fwd_composite: S=%lld is not served by the fused epilogue "
+             "(see fnerf_mlp_fwd_composite_supported)", (long long)S);
+  MlpArgs a{packed, cond ? 1 : 0, rays_o, rays_d, viewdirs, z, cond_proj, cond_index, C, raw, R, S};
+  CompositeOut c{dnorm, raw_noise, rgb, depth, acc, disp, weights, white_bkgd};
+  return launch_mlp_tc_composite(a, c, (cudaStream_t)stream);
+}
+
 int64_t fnerf_mlp_tape_bytes(int64_t R, int64_t S) { return mlp_tape_bytes(R * S); }
 int64_t fnerf_mlp_bwd_tape_workspace_bytes(int64_t R, int64_t S) { return mlp_bwd_from_tape_workspace_bytes(R * S); }
 
@@ -297,35 +315,51 @@ int fnerf_render_rays(const fnerf_render_args* a, fnerf_stream_t stream) {
   };
   if ((rc = fnerf_ray_setup(a->rays_d, viewdirs, dnorm, R, stream))) return rc;
   if ((rc = fnerf_stratified(a->near, a->far, a->t_vals, a->u_strat, z_c, R, Nc, a->lindisp, stream))) return rc;
+  // fused path: compositing inside the network-query kernel, raw[R,S,4] written only if the caller asks
+  // for the tap.  bf16 inference only (the training tape keeps the separate kernels: the backward needs raw anyway).
+  const bool fuse_c = a->fuse_composite && a->precision == FNERF_PRECISION_BF16 && !a->tape_coarse && mlp_tc_composite_group(Nc) > 0;
+  const bool fuse_f = Nf > 0 && a->fuse_composite && a->precision == FNERF_PRECISION_BF16 && !a->tape_fine && mlp_tc_composite_group(Nc + Nf) > 0;
   if ((rc = record(a->ev_coarse_start))) return rc;
-  if (a->tape_coarse) {
+  if (fuse_c) {
+    float* rgb_c = Nf == 0 ? a->rgb : a->rgb0;
+    float* dep_c = Nf == 0 ? a->depth : depth0;
+    float* acc_c = Nf == 0 ? a->acc : a->acc0;
+    float* dis_c = Nf == 0 ? a->disp : a->disp0;
+    if ((rc = fnerf_mlp_fwd_composite(a->packed_coarse, a->cond, a->rays_o, a->rays_d, viewdirs, dnorm, z_c, a->cond_proj_coarse,
+                                      a->cond_index, a->C, a->raw_noise_coarse, a->raw_c, rgb_c, dep_c, acc_c, dis_c,
+                                      (Nf > 0 || a->weights_c) ? weights_c : nullptr, R, Nc, a->white_bkgd, stream))) return rc;
+  } else if (a->tape_coarse) {
     if ((rc = fnerf_mlp_fwd_tape(a->packed_coarse, a->cond, a->rays_o, a->rays_d, viewdirs, z_c, a->cond_proj_coarse,
                                  a->cond_index, a->C, raw_c, a->tape_coarse, a->tape_coarse_bytes, R, Nc, stream))) return rc;
   } else if ((rc = fnerf_mlp_fwd(a->precision, a->packed_coarse, a->cond, a->rays_o, a->rays_d, viewdirs, z_c,
                                  a->cond_proj_coarse, a->cond_index, a->C, raw_c, R, Nc, stream))) return rc;
   if ((rc = record(a->ev_coarse_stop))) return rc;
   if (Nf == 0) {
-    if ((rc = fnerf_composite_fwd(raw_c, z_c, dnorm, a->raw_noise_coarse, a->rgb, a->depth, a->acc, a->disp,
-                                  a->weights_c ? weights_c : nullptr, R, Nc, a->white_bkgd, stream))) return rc;
+    if (!fuse_c && (rc = fnerf_composite_fwd(raw_c, z_c, dnorm, a->raw_noise_coarse, a->rgb, a->depth, a->acc, a->disp,
+                                             a->weights_c ? weights_c : nullptr, R, Nc, a->white_bkgd, stream))) return rc;
     if ((rc = d2d(a->rgb0, a->rgb, R * 3)) || (rc = d2d(a->disp0, a->disp, R)) || (rc = d2d(a->acc0, a->acc, R))) return rc;
     if (a->depth0 && (rc = d2d(a->depth0, a->depth, R))) return rc;
     if (cudaError_t e = cudaMemsetAsync(a->z_std, 0, R * sizeof(float), s))
       return set_error((int)e, "render_rays: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return check_launch("render_rays");
   }
-  if ((rc = fnerf_composite_fwd(raw_c, z_c, dnorm, a->raw_noise_coarse, a->rgb0, depth0, a->acc0, a->disp0, weights_c, R, Nc,
-                                a->white_bkgd, stream))) return rc;
+  if (!fuse_c && (rc = fnerf_composite_fwd(raw_c, z_c, dnorm, a->raw_noise_coarse, a->rgb0, depth0, a->acc0, a->disp0, weights_c, R, Nc,
+                                           a->white_bkgd, stream))) return rc;
   if ((rc = fnerf_importance(z_c, weights_c, a->u_fine, a->u_fine_row_stride, z_samples, z_f, nullptr, a->z_std,
                              R, Nc, Nf, stream))) return rc;
   if ((rc = record(a->ev_fine_start))) return rc;
-  if (a->tape_fine) {
+  if (fuse_f) {
+    if ((rc = fnerf_mlp_fwd_composite(a->packed_fine, a->cond, a->rays_o, a->rays_d, viewdirs, dnorm, z_f, a->cond_proj_fine,
+                                      a->cond_index, a->C, a->raw_noise_fine, a->raw_f, a->rgb, a->depth, a->acc, a->disp, a->weights_f,
+                                      R, Nc + Nf, a->white_bkgd, stream))) return rc;
+  } else if (a->tape_fine) {
     if ((rc = fnerf_mlp_fwd_tape(a->packed_fine, a->cond, a->rays_o, a->rays_d, viewdirs, z_f, a->cond_proj_fine,
                                  a->cond_index, a->C, raw_f, a->tape_fine, a->tape_fine_bytes, R, Nc + Nf, stream))) return rc;
   } else if ((rc = fnerf_mlp_fwd(a->precision, a->packed_fine, a->cond, a->rays_o, a->rays_d, viewdirs, z_f,
                                  a->cond_proj_fine, a->cond_index, a->C, raw_f, R, Nc + Nf, stream))) return rc;
   if ((rc = record(a->ev_fine_stop))) return rc;
-  if ((rc = fnerf_composite_fwd(raw_f, z_f, dnorm, a->raw_noise_fine, a->rgb, a->depth, a->acc, a->disp, a->weights_f, R,
-                                Nc + Nf, a->white_bkgd, stream))) return rc;
+  if (!fuse_f && (rc = fnerf_composite_fwd(raw_f, z_f, dnorm, a->raw_noise_fine, a->rgb, a->depth, a->acc, a->disp, a->weights_f, R,
+                                           Nc + Nf, a->white_bkgd, stream))) return rc;
   return 0;
 }
 

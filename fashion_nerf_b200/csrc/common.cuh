@@ -95,6 +95,14 @@ struct MlpArgs {
   const float* cond_proj; const int32_t* cond_index; int64_t C;
   float* raw; int64_t R, S;
 };
+// outputs / extra inputs of the network query with fused compositing (mlp_tc.cu)
+struct CompositeOut {
+  const float* dnorm; const float* noise;
+  float* rgb; float* depth; float* acc; float* disp; float* weights;
+  int white;
+};
+int mlp_tc_composite_group(int64_t S);
+int launch_mlp_tc_composite(const MlpArgs& a, const CompositeOut& c, cudaStream_t s);
 int launch_mlp_fp32(const MlpArgs& a, cudaStream_t s);
 int launch_mlp_tc(const MlpArgs& a, cudaStream_t s);
 int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cudaStream_t s);   // training forward: also writes the tape

@@ -6,19 +6,11 @@
 // and a scalar carry between blocks.  The kernels are HBM-bound: 24S+36 B/ray forward,
 // 36S+24 B/ray backward.
 #include "common.cuh"
+#include "composite_math.cuh"
 
 namespace fnerf {
 
 constexpr int kCompWarps = 8;
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// sigmoid through ex2.approx + rcp-based division (~6 instructions instead of ~30): relative error ~3e-7, which
-// enters the maps linearly (weights sum to <= 1); the transmittance product keeps the exact expf
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
   float4 v;
@@ -50,7 +42,7 @@ k_composite_fwd(const float4* __restrict__ raw, const float* __restrict__ z,
     const float* zr = z + r * S;
     const float dn = dnorm[r];
     float carry = 1.0f;                       // transmittance entering this 32-sample block
-    float a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
+    CompSums a = {0.f, 0.f, 0.f, 0.f, 0.f};
 
     // software pipeline: the next block's loads are issued before this block's scan
     int i = lane;
@@ -72,43 +64,18 @@ k_composite_fwd(const float4* __restrict__ raw, const float* __restrict__ z,
       dist *= dn;
       float sigma = rv.w;
       if (kHasNoise) sigma += nz;
-      const float alpha = valid ? (1.0f - expf(-fmaxf(sigma, 0.0f) * dist)) : 0.0f;
-      const float om = valid ? (1.0f - alpha + 1e-10f) : 1.0f;
-
-      float p = om;                           // inclusive product scan
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float n = __shfl_up_sync(0xffffffffu, p, o);
-        if (lane >= o) p *= n;
-      }
-      float excl = __shfl_up_sync(0xffffffffu, p, 1);
-      if (lane == 0) excl = 1.0f;
-      const float T = carry * excl;
-      const float w = alpha * T;
+      const float alpha = comp_alpha(sigma, dist, valid);
+      const float p = comp_scan(alpha, valid, lane);
+      const float w = comp_weight(alpha, p, carry, lane);
       carry *= __shfl_sync(0xffffffffu, p, 31);
 
       if (valid) {
-        a_r += w * sigmoidf_(rv.x);
-        a_g += w * sigmoidf_(rv.y);
-        a_b += w * sigmoidf_(rv.z);
-        a_d += w * zv;
-        a_w += w;
+        comp_accum(a, w, sigmoidf_(rv.x), sigmoidf_(rv.y), sigmoidf_(rv.z), zv);
         if (weights != nullptr) weights[r * S + i] = w;
       }
       rv = rv_n; zv = zv_n; nz = nz_n; i = inext;
     }
-    a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);
-    a_d = warp_sum(a_d); a_w = warp_sum(a_w);
-    if (lane == 0) {
-      const float bg = white ? (1.0f - a_w) : 0.0f;
-      rgb_out[3 * r] = a_r + bg;
-      rgb_out[3 * r + 1] = a_g + bg;
-      rgb_out[3 * r + 2] = a_b + bg;
-      depth_out[r] = a_d;
-      acc_out[r] = a_w;
-      const float q = a_d / a_w;              // NaN when acc == 0: propagated like torch.max does
-      disp_out[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
-    }
+    comp_finish(a, lane, r, white, rgb_out, depth_out, acc_out, disp_out);
   }
 }
 
@@ -140,7 +107,8 @@ k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
       }
     }
     const float dn = dnorm[r];
-    float carry = 1.0f, a_r = 0.f, a_g = 0.f, a_b = 0.f, a_d = 0.f, a_w = 0.f;
+    float carry = 1.0f;
+    CompSums a = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       const int i = b * 32 + lane;
@@ -151,39 +119,17 @@ k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
         const bool valid = i < S;
         float dist = (i == S - 1) ? 1e10f : (z_up - zv[b]);
         dist *= dn;
-        const float alpha = valid ? (1.0f - expf(-fmaxf(rv[b].w, 0.0f) * dist)) : 0.0f;
-        float p = valid ? (1.0f - alpha + 1e-10f) : 1.0f;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const float n = __shfl_up_sync(0xffffffffu, p, o);
-          if (lane >= o) p *= n;
-        }
-        float excl = __shfl_up_sync(0xffffffffu, p, 1);
-        if (lane == 0) excl = 1.0f;
-        const float w = alpha * (carry * excl);
+        const float alpha = comp_alpha(rv[b].w, dist, valid);
+        const float p = comp_scan(alpha, valid, lane);
+        const float w = comp_weight(alpha, p, carry, lane);
         carry *= __shfl_sync(0xffffffffu, p, 31);
         if (valid) {
-          a_r += w * sigmoidf_(rv[b].x);
-          a_g += w * sigmoidf_(rv[b].y);
-          a_b += w * sigmoidf_(rv[b].z);
-          a_d += w * zv[b];
-          a_w += w;
+          comp_accum(a, w, sigmoidf_(rv[b].x), sigmoidf_(rv[b].y), sigmoidf_(rv[b].z), zv[b]);
           if (weights != nullptr) weights[r * S + i] = w;
         }
       }
     }
-    a_r = warp_sum(a_r); a_g = warp_sum(a_g); a_b = warp_sum(a_b);
-    a_d = warp_sum(a_d); a_w = warp_sum(a_w);
-    if (lane == 0) {
-      const float bg = white ? (1.0f - a_w) : 0.0f;
-      rgb_out[3 * r] = a_r + bg;
-      rgb_out[3 * r + 1] = a_g + bg;
-      rgb_out[3 * r + 2] = a_b + bg;
-      depth_out[r] = a_d;
-      acc_out[r] = a_w;
-      const float q = a_d / a_w;              // NaN when acc == 0: propagated like torch.max does
-      disp_out[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
-    }
+    comp_finish(a, lane, r, white, rgb_out, depth_out, acc_out, disp_out);
   }
 }
 

@@ -30,6 +30,7 @@
 // and of the view layer.
 #include <stdlib.h>
 #include "common.cuh"
+#include "composite_math.cuh"
 #include "tc_ptx.cuh"
 
 namespace fnerf {
@@ -51,7 +52,9 @@ constexpr uint32_t kOffHeads = kOffW + kStages * kBigChunkBytes;  // fp32 head w
 constexpr int kHeadFloats = kAuxFloats - kAuxWAlpha;
 constexpr uint32_t kOffBar = kOffHeads + kHeadFloats * 4;
 constexpr uint32_t kNumBars = 3 * (2 * kStages) + 4 + 1 + 2;   // room for the pair mode: 2*kStages x (full, empty, peer-weights) + act-ready, encodings, acc-full
-constexpr uint32_t kTcSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;  // + tmem ptr + alignment slack
+constexpr uint32_t kOffComp = kOffBar + kNumBars * 8 + 16;   // fused compositing (kComp): block products + tile carry, running sums, block operands
+constexpr uint32_t kCompFloats = 32 + 5 * 32 + 4 * 6 * 32;
+constexpr uint32_t kTcSmemBytes = kOffComp + kCompFloats * 4 + 1024;  // + alignment slack
 static_assert(kOffBar % 8 == 0, "barrier alignment");
 static_assert(kTcSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -97,6 +100,12 @@ struct TcParams {
   int64_t M; int S; int64_t ntiles; int cond;
   uint8_t* tape;        // kSave only: per tile kTapeFwdSlots K-block images (layout.h), the shared-memory bytes verbatim
   uint32_t* mask_tape;  // kSave only: per tile kMaskUnits x 128 ReLU bitmask words (layout.h)
+  // kComp only: alpha compositing (A.5) fused into the last epilogue.  Tiles are walked in GROUPS of `gt` consecutive
+  // tiles that hold whole rays (gt * 128 = rays_per_group * S), so transmittance and the ray sums never leave the CTA.
+  const float* dnorm; const float* noise;          // [R]; [R,S] nullable
+  float* rgb_map; float* depth_map; float* acc_map; float* disp_map;   // [R,3], [R], [R], [R]
+  float* weights;                                   // [R,S] nullable
+  int gt; int rays_per_group; int white;
 };
 
 // two non-negative bf16 in one word -> bit 0 = (low half != 0), bit 16 = (high half != 0): adding 0x7FFF to a
@@ -165,7 +174,7 @@ __device__ __forceinline__ void pair_bar_sync(uint32_t pair) { asm volatile("bar
 // act-ready and encoding barriers (mbarrier.arrive.release.cluster on mapa addresses); the peer's otherwise idle MMA warp
 // relays "my half of stage s has landed" to the leader; tcgen05.commit multicasts stage-empty and accumulator-full to
 // both CTAs.  Both CTAs run the same number of tiles (a tile past the end is computed on clamped inputs, not stored).
-template <bool kSave, int kCl>
+template <bool kSave, int kCl, bool kComp = false>
 __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -197,6 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     *reinterpret_cast<unsigned short*>(base_ptr + kOffOnes + bias_chunk_offset(m, k)) =
         (k == (uint32_t)(kBiasColHi - 16) || k == (uint32_t)(kBiasColLo - 16)) ? (unsigned short)0x3F80 : (unsigned short)0;
   }
+  if (kComp && threadIdx.x < 32 + 5 * 32) reinterpret_cast<float*>(base_ptr + kOffComp)[threadIdx.x] = threadIdx.x == 4 ? 1.0f : 0.0f;
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSt; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); mbar_init(bar_wpeer(s), 1); }
@@ -219,8 +229,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   const int64_t first_tile = blockIdx.x;
   const int64_t tile_stride = gridDim.x;
   // every CTA runs n_iter tiles (identical across a cluster); without clusters that is exactly the tiles it owns
-  const int64_t n_iter = kCl > 1 ? (P.ntiles + tile_stride - 1) / tile_stride
-                                 : (P.ntiles > first_tile ? (P.ntiles - first_tile + tile_stride - 1) / tile_stride : 0);
+  int64_t n_iter = kCl > 1 ? (P.ntiles + tile_stride - 1) / tile_stride
+                           : (P.ntiles > first_tile ? (P.ntiles - first_tile + tile_stride - 1) / tile_stride : 0);
+  // kComp: the CTA owns whole groups of gt consecutive tiles (groups blockIdx.x, + gridDim.x, ...); only the last group of
+  // the launch can be short
+  const int64_t gt = kComp ? P.gt : 1;
+  if (kComp) {
+    const int64_t ngroups = (P.ntiles + gt - 1) / gt;
+    const int64_t mine = ngroups > first_tile ? (ngroups - first_tile + tile_stride - 1) / tile_stride : 0;
+    n_iter = mine * gt;
+    if (mine > 0 && first_tile + (mine - 1) * tile_stride == ngroups - 1) n_iter -= ngroups * gt - P.ntiles;
+  }
+  auto tile_of = [&](int64_t it) -> int64_t {
+    if (!kComp) return first_tile + it * tile_stride;
+    return (first_tile + (it / gt) * tile_stride) * gt + it % gt;
+  };
   [[maybe_unused]] const uint32_t cta_rank = kCl > 1 ? cluster_ctarank() : 0u;
   constexpr uint16_t kClMask = (uint16_t)((1u << kCl) - 1u);
   // pair mode: act-ready / encoding arrivals of BOTH CTAs go to the leader's barriers
@@ -232,7 +255,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     if (lane == 0) {
       uint32_t wc = 0;
       for (int64_t it = 0; it < n_iter; ++it) {
-        [[maybe_unused]] const int64_t tile = first_tile + it * tile_stride;
+        [[maybe_unused]] const int64_t tile = tile_of(it);
         uint32_t coff = 0;                       // chunk_offset(c), accumulated
         for (int c = 0; c < kNumChunks; ++c, ++wc) {
           const uint32_t s = wc % kSt;
@@ -406,8 +429,76 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
       if (kCl > 1) mbar_arrive_cluster(lead_bar_pe);
       else mbar_arrive(bar_pe);
     };
+    // ---- alpha compositing (A.5) of the PREVIOUS tile's 128 samples (kComp; finishing group only) --------------------
+    // S % 32 == 0, so a warp holds one 32-sample block of ONE ray: exactly the unit the stand-alone kernel (composite.cu)
+    // walks.  Same per-sample arithmetic (composite_math.cuh), same order -- the transmittance entering a block is the
+    // sequential product of the blocks before it, every lane adds its samples block after block, one warp reduction per
+    // ray -- so the maps and weights carry the stand-alone kernel's bits whatever the alignment of rays to tiles.  A ray
+    // that spans tiles hands over through shared memory.  The work is cut into three short phases that run after the
+    // group's first three layer epilogues of the next tile, where the group would otherwise wait for an accumulator:
+    // done in one piece at the end of its own tile it delays the next tile's first layers (+3 % per launch, measured).
+    [[maybe_unused]] auto comp_phase = [&](int ph) {
+      float* cs = reinterpret_cast<float*>(base_ptr + kOffComp);
+      float* s_P = cs;                       // [4]  product of (1 - alpha + 1e-10) over each warp's block
+      float* s_carry = cs + 4;               // [2]  transmittance entering the tile (ray continued from the one before); its successor
+      float* s_run = cs + 32;                // [5][32] per-lane sums of that ray so far
+      float* s_ops = cs + 32 + 5 * 32;       // [4][6][32] the tile's blocks: alpha -> w, sigmoid(r,g,b), z, inclusive scan per lane
+      asm volatile("bar.sync 4, 128;" ::: "memory");
+      const int S = P.S;
+      const int64_t t0 = reinterpret_cast<const long long*>(cs + 8)[0] * (int64_t)kTileM;
+      const int k0 = reinterpret_cast<const int*>(cs + 6)[0];           // sample index in its ray of the tile's first row
+      const int64_t pray = reinterpret_cast<const long long*>(cs + 10)[q];
+      auto blk_k = [&](uint32_t w) { return (int)((uint32_t)(k0 + 32 * (int)w) % (uint32_t)S); };
+      const int ck = blk_k(q);
+      const bool bvalid = t0 + 32 * q < P.M;                            // M % 32 == 0: a block is valid as a whole
+      const bool btail = ck + 32 == S;
+      const int64_t pg = t0 + row;
+      float* o = s_ops + q * (6 * 32) + lane;
+      if (ph == 1) {
+        const int64_t pgc = bvalid ? pg : P.M - 1;
+        const float zv = P.z[pgc];
+        float z_up = __shfl_down_sync(0xffffffffu, zv, 1);
+        if (lane == 31 && !btail) z_up = P.z[pgc + 1 < P.M ? pgc + 1 : pgc];
+        float dist = (lane == 31 && btail) ? 1e10f : (z_up - zv);
+        dist *= P.dnorm[pray];
+        const float4 fin = *reinterpret_cast<const float4*>(ped_row_ptr + ((4u ^ (row & 7u)) << 4));
+        float sgm = fin.w;
+        if (P.noise != nullptr) sgm += P.noise[pgc];
+        const float alpha = comp_alpha(sgm, dist, bvalid);
+        const float pin = comp_scan(alpha, bvalid, (int)lane);
+        if (lane == 31) s_P[q] = pin;
+        o[0] = alpha; o[32] = sigmoidf_(fin.x); o[64] = sigmoidf_(fin.y); o[96] = sigmoidf_(fin.z); o[128] = zv; o[160] = pin;
+      } else if (ph == 2) {
+        // transmittance entering this block: the chain restarts at a ray head, else continues the previous block's
+        float carry = (k0 == 0) ? 1.0f : s_carry[0];
+        for (uint32_t w2 = 0; w2 < q; ++w2) {
+          carry *= s_P[w2];
+          if (blk_k(w2 + 1) == 0) carry = 1.0f;
+        }
+        const float pin = o[160];
+        const float w = comp_weight(o[0], pin, carry, (int)lane);
+        if (P.weights != nullptr && bvalid) P.weights[pg] = w;
+        o[0] = w;
+        if (q == 3 && lane == 31) s_carry[1] = carry * pin;             // becomes s_carry[0] once every warp has read the old one
+      } else {
+        // the warp holding a ray's last block in this tile adds up the ray's blocks of this tile, in order, on top of
+        // what earlier tiles left; it finishes the ray or leaves the sums for the next tile
+        if (bvalid && (btail || q == 3)) {
+          int first = (int)q - ck / 32;                                 // block of this tile where the ray starts (< 0: earlier tile)
+          CompSums a = {0.f, 0.f, 0.f, 0.f, 0.f};
+          if (first < 0) { first = 0; a.r = s_run[lane]; a.g = s_run[32 + lane]; a.b = s_run[64 + lane]; a.d = s_run[96 + lane]; a.w = s_run[128 + lane]; }
+          for (int w2 = first; w2 <= (int)q; ++w2) {
+            const float* ow = s_ops + w2 * (6 * 32) + lane;
+            comp_accum(a, ow[0], ow[32], ow[64], ow[96], ow[128]);
+          }
+          if (btail) comp_finish(a, (int)lane, pray, P.white, P.rgb_map, P.depth_map, P.acc_map, P.disp_map);
+          else { s_run[lane] = a.r; s_run[32 + lane] = a.g; s_run[64 + lane] = a.b; s_run[96 + lane] = a.d; s_run[128 + lane] = a.w; }
+        }
+        if (q == 3 && lane == 31) s_carry[0] = s_carry[1];
+      }
+    };
     for (int64_t it = 0; it < n_iter; ++it) {
-      const int64_t tile = first_tile + it * tile_stride;     // >= ntiles only in a cluster's padding tiles: g >= M, nothing stored
+      const int64_t tile = tile_of(it);     // >= ntiles only in a cluster's padding tiles: g >= M, nothing stored
       const int64_t g = tile * kTileM + row;
       const int64_t gc = g < P.M ? g : P.M - 1;
       const int64_t ray = gc / P.S;
@@ -514,7 +605,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         }
         // next tile's xyz encodings, in the shadow of layer 1's MMAs (the buffer's last reader, layer 5 of the tile
         // before this one, completed long ago)
-        if (step == 0 && grp == 0 && it + 1 < n_iter) compute_pe(tile + tile_stride, (uint32_t)((it + 1) & 1));
+        if (step == 0 && grp == 0 && it + 1 < n_iter) compute_pe(tile_of(it + 1), (uint32_t)((it + 1) & 1));
+        if (kComp && grp == 3 && step < 3 && it > 0) comp_phase(step + 1);
       }
       // ---- view layer epilogue + rgb head: each group reduces 32 of the 128 columns ---------------
       {
@@ -550,25 +642,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           mask_row[(kMaskUnitHv + (int)grp) * 128] = mask;
         }
         tc_fence_before();
-        // partials of groups 1..3 park in the unused upper half (logical chunks 5..7) of this row of
-        // the direction tile; the view layer's MMAs (its last async-proxy readers this tile) are complete
-        if (grp != 0) *reinterpret_cast<float4*>(ped_row_ptr + (((4u + grp) ^ (row & 7u)) << 4)) = make_float4(c0, c1, c2, sigma);
+        // The partials of three groups park in logical chunks 5..7 of this row of the direction tile (its unused upper
+        // half; the view layer's MMAs, its last async-proxy readers this tile, are complete); the fourth group sums them.
+        // That group is 0 in the plain kernel and 3 when compositing is fused in (group 0 already builds the next tile's
+        // xyz encodings); chunk 4 + grp with the roles of 0 and kFin swapped.
+        constexpr uint32_t kFin = kComp ? 3u : 0u;
+        const uint32_t park = grp == 0 ? kFin : grp;          // group 0 parks in the finishing group's chunk when it is not the finisher
+        if (grp != kFin) *reinterpret_cast<float4*>(ped_row_ptr + (((4u + park) ^ (row & 7u)) << 4)) = make_float4(c0, c1, c2, sigma);
         worker_bar_sync();
-        if (grp == 0) {
+        if (grp == kFin) {
+          // chunks 5, 6 hold groups 1, 2; chunk 7 holds group 3 (plain kernel) or group 0 (kComp).  The sum is always
+          // (g0 + g1) + (g2 + g3): fp32 addition commutes, so both kernels produce the same bits
           const float4 p1 = *reinterpret_cast<const float4*>(ped_row_ptr + ((5u ^ (row & 7u)) << 4));
           const float4 p2 = *reinterpret_cast<const float4*>(ped_row_ptr + ((6u ^ (row & 7u)) << 4));
-          const float4 p3 = *reinterpret_cast<const float4*>(ped_row_ptr + ((7u ^ (row & 7u)) << 4));
+          float4 p3 = *reinterpret_cast<const float4*>(ped_row_ptr + ((7u ^ (row & 7u)) << 4));
+          if (kComp) {                                        // own partial takes group 3's place, group 0's takes "own"
+            const float4 own = make_float4(c0, c1, c2, sigma);
+            c0 = p3.x; c1 = p3.y; c2 = p3.z; sigma = p3.w;
+            p3 = own;
+          }
           const float* brgb = heads_s + (kAuxBRgb - kAuxWAlpha);
           c0 = brgb[0] + ((c0 + p1.x) + (p2.x + p3.x));
           c1 = brgb[1] + ((c1 + p1.y) + (p2.y + p3.y));
           c2 = brgb[2] + ((c2 + p1.z) + (p2.z + p3.z));
           const float sg = heads_s[kAuxBAlpha - kAuxWAlpha] + ((sigma + p1.w) + (p2.w + p3.w));
           // streaming store: raw is gigabytes per frame, read once by compositing
-          if (g < P.M) asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.raw + g), "f"(c0), "f"(c1), "f"(c2), "f"(sg) : "memory");
+          if (g < P.M && (!kComp || P.raw != nullptr))
+            asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(P.raw + g), "f"(c0), "f"(c1), "f"(c2), "f"(sg) : "memory");
+          if (kComp) {
+            // hand the tile to the compositing phases, which run inside the NEXT tile (comp_phase): final raw values in the
+            // free chunk 4 of this row of the direction tile, the tile's coordinates next to the running sums
+            *reinterpret_cast<float4*>(ped_row_ptr + ((4u ^ (row & 7u)) << 4)) = make_float4(c0, c1, c2, sg);
+            float* cs = reinterpret_cast<float*>(base_ptr + kOffComp);
+            if (lane == 0) reinterpret_cast<long long*>(cs + 10)[q] = ray;
+            if (row == 0) { reinterpret_cast<long long*>(cs + 8)[0] = tile; reinterpret_cast<int*>(cs + 6)[0] = (int)(gc - ray * (int64_t)P.S); }
+          }
         }
       }
       ++wtile;
     }
+    if (kComp && grp == 3 && n_iter > 0) { comp_phase(1); comp_phase(2); comp_phase(3); }     // the CTA's last tile
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
@@ -660,5 +773,39 @@ int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cud
 }
 
 int launch_mlp_tc(const MlpArgs& a, cudaStream_t s) { return launch_mlp_tc_tape(a, nullptr, nullptr, s); }
+
+// Tiles per whole-ray group for a sample count S (gt * 128 = rays * S), or 0 when the fused compositing epilogue cannot
+// serve S: a warp must hold 32 samples of one ray (S % 32 == 0), and a group is capped at 16 tiles so that the static
+// round-robin of groups over the CTAs stays balanced.
+int mlp_tc_composite_group(int64_t S) {
+  if (S < 1) return 0;
+  int64_t a = S, b = kTileM;
+  while (b) { const int64_t t = a % b; a = b; b = t; }          // a = gcd(S, 128)
+  const int64_t gt = S / a;
+  return (S % 32 == 0 && gt <= 16) ? (int)gt : 0;
+}
+
+// Network query with alpha compositing (A.5) fused into the last epilogue: raw[R,S,4] is written only when a.raw != NULL.
+int launch_mlp_tc_composite(const MlpArgs& a, const CompositeOut& c, cudaStream_t s) {
+  const int64_t M = a.R * a.S;
+  if (M == 0) return 0;
+  const int gt = mlp_tc_composite_group(a.S);
+  if (gt == 0) return set_error(FNERF_ERR_SIZE, "mlp_fwd_composite: S=%lld has no whole-ray tile group", (long long)a.S);
+  static DeviceOnce once;
+  if (cudaError_t e = opt_in_smem_once(once, k_mlp_tc<false, 1, true>, kTcSmemBytes)) return set_error((int)e, "mlp_tc attr: %s", cudaGetErrorString(e));
+  TcParams P = {};
+  P.packed = reinterpret_cast<const uint8_t*>(a.packed);
+  P.rays_o = a.rays_o; P.rays_d = a.rays_d; P.viewdirs = a.viewdirs; P.z = a.z;
+  P.cond_proj = a.cond_proj; P.cond_index = a.cond_index; P.C = a.C;
+  P.raw = reinterpret_cast<float4*>(a.raw);
+  P.M = M; P.S = (int)a.S; P.ntiles = (M + kTileM - 1) / kTileM; P.cond = a.cond;
+  P.dnorm = c.dnorm; P.noise = c.noise; P.rgb_map = c.rgb; P.depth_map = c.depth; P.acc_map = c.acc; P.disp_map = c.disp;
+  P.weights = c.weights; P.gt = gt; P.rays_per_group = (int)((int64_t)gt * kTileM / a.S); P.white = c.white;
+  const int64_t ngroups = (P.ntiles + gt - 1) / gt;
+  int64_t blocks = num_sms();
+  if (blocks > ngroups) blocks = ngroups;
+  k_mlp_tc<false, 1, true><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
+  return check_launch("mlp_tc_composite");
+}
 
 }  // namespace fnerf

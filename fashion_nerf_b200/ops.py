@@ -134,6 +134,43 @@ def mlp_fwd(packed: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, vi
     return raw
 
 
+def mlp_fwd_composite_supported(S: int) -> bool:
+    """True when the fused query + compositing kernel serves S samples per ray (whole-ray tile groups, include/fnerf.h)."""
+    return bool(_lib.load().fnerf_mlp_fwd_composite_supported(int(S)))
+
+
+def mlp_fwd_composite(packed: torch.Tensor, rays_o, rays_d, viewdirs, dnorm, z, *, cond_proj=None, cond_index=None,
+                      raw_noise: Optional[torch.Tensor] = None, white_bkgd: bool = False, want_raw: bool = False,
+                      want_weights: bool = True):
+    """bf16 network query with A.5 fused into its last epilogue (SURVEY.md 8f-1): dict(rgb, depth, acc, disp, weights, raw);
+    raw[R,S,4] is only produced (and only touches HBM) when want_raw."""
+    rays_o, rays_d, viewdirs, dnorm, z = (_f32(rays_o, "rays_o"), _f32(rays_d, "rays_d"), _f32(viewdirs, "viewdirs"),
+                                          _f32(dnorm, "dnorm"), _f32(z, "z"))
+    R, S = z.shape
+    dev = z.device
+    if raw_noise is not None:
+        raw_noise = _f32(raw_noise, "raw_noise")
+        assert raw_noise.shape == (R, S)
+    has_cond = cond_proj is not None
+    C = cond_proj.shape[0] if has_cond else 0
+    if cond_index is not None:
+        cond_index = cond_index.to(torch.int32).contiguous()
+
+    def new(*shape):
+        return torch.empty(*shape, dtype=torch.float32, device=dev)
+
+    raw = new(R, S, 4) if want_raw else None
+    weights = new(R, S) if want_weights else None
+    rgb, depth, acc, disp = new(R, 3), new(R), new(R), new(R)
+    with torch.cuda.device(dev):
+        check(_lib.load().fnerf_mlp_fwd_composite(packed.data_ptr(), int(has_cond), rays_o.data_ptr(), rays_d.data_ptr(),
+                                                  viewdirs.data_ptr(), dnorm.data_ptr(), z.data_ptr(), _ptr(cond_proj),
+                                                  _ptr(cond_index), C, _ptr(raw_noise), _ptr(raw), rgb.data_ptr(),
+                                                  depth.data_ptr(), acc.data_ptr(), disp.data_ptr(), _ptr(weights), R, S,
+                                                  int(white_bkgd), _stream()), "mlp_fwd_composite")
+    return {"rgb": rgb, "depth": depth, "acc": acc, "disp": disp, "weights": weights, "raw": raw}
+
+
 def mlp_bwd(packed: torch.Tensor, rays_o, rays_d, viewdirs, z, g_raw: torch.Tensor, flat_grad: torch.Tensor, *,
             precision: str = "fp32", cond_rows=None, cond_index=None) -> torch.Tensor:
     """Accumulates dL/dparams into flat_grad (flat layout) given g_raw[R,S,4].  cond_rows: RAW codes [C,256]."""

@@ -40,7 +40,7 @@ def _linspace01(n: int, device) -> torch.Tensor:
 
 
 def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, noise_c, noise_f, cond_proj_c,
-                 cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision, save_tape=False) -> List[_T]:
+                 cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision, save_tape=False, fuse=False, taps=True) -> List[_T]:
     lib = _lib.load()
     dev = rays_o.device
     R, Nc, Nf = rays_o.shape[0], t_vals.numel(), int(n_importance)
@@ -51,8 +51,10 @@ def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat,
 
     rgb, disp, acc, depth = new(R, 3), new(R), new(R), new(R)
     rgb0, disp0, acc0, z_std, depth0 = new(R, 3), new(R), new(R), new(R), new(R)
-    z_c, raw_c, w_c = new(R, Nc), new(R, Nc, 4), new(R, Nc)
-    z_f, raw_f = (new(R, S), new(R, S, 4)) if Nf > 0 else (new(0), new(0))
+    # fused compositing without taps: raw[R,S,4] is neither allocated nor written
+    want_raw = taps or not fuse
+    z_c, raw_c, w_c = new(R, Nc), (new(R, Nc, 4) if want_raw else new(0)), new(R, Nc)
+    z_f, raw_f = (new(R, S), (new(R, S, 4) if want_raw else new(0))) if Nf > 0 else (new(0), new(0))
     ws_bytes = int(lib.fnerf_render_rays_workspace_bytes(R, Nc, Nf))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
 
@@ -73,10 +75,13 @@ def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat,
     a.rgb, a.disp, a.acc, a.depth = rgb.data_ptr(), disp.data_ptr(), acc.data_ptr(), depth.data_ptr()
     a.rgb0, a.disp0, a.acc0, a.z_std = rgb0.data_ptr(), disp0.data_ptr(), acc0.data_ptr(), z_std.data_ptr()
     a.depth0 = depth0.data_ptr()
-    a.z_c, a.raw_c, a.weights_c = z_c.data_ptr(), raw_c.data_ptr(), w_c.data_ptr()
+    a.z_c, a.weights_c = z_c.data_ptr(), w_c.data_ptr()
+    a.raw_c = raw_c.data_ptr() if want_raw else None
     if Nf > 0:
-        a.z_f, a.raw_f = z_f.data_ptr(), raw_f.data_ptr()
+        a.z_f = z_f.data_ptr()
+        a.raw_f = raw_f.data_ptr() if want_raw else None
     a.weights_f = None
+    a.fuse_composite = int(fuse)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     # training forward: activations taped for the tensor-core backward.  The tapes are op OUTPUTS (uint8, hence
     # non-differentiable: autograd never materialises gradients for them) that only the autograd node keeps alive.
@@ -98,34 +103,36 @@ def _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat,
 def render_rays_op(flat_c: _T, flat_f: _T, packed_c: _T, packed_f: _T, rays_o: _T, rays_d: _T, near: _T, far: _T,
                    t_vals: _T, u_strat: Optional[_T], u_fine: Optional[_T], noise_c: Optional[_T], noise_f: Optional[_T],
                    cond_proj_c: Optional[_T], cond_proj_f: Optional[_T], cond_index: Optional[_T], cond_rows: Optional[_T],
-                   n_importance: int, white_bkgd: bool, lindisp: bool, precision: int, save_tape: bool) -> List[_T]:
+                   n_importance: int, white_bkgd: bool, lindisp: bool, precision: int, save_tape: bool, fuse: bool,
+                   taps: bool) -> List[_T]:
     # flat_c / flat_f only anchor the autograd graph (and cond_rows only feeds the backward); the
     # forward kernels read the packed blobs and the hoisted projections.
     return _render_impl(packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, noise_c, noise_f, cond_proj_c,
-                        cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision, save_tape)
+                        cond_proj_f, cond_index, n_importance, white_bkgd, lindisp, precision, save_tape, fuse, taps)
 
 
 @render_rays_op.register_fake
 def _(flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, noise_c, noise_f, cond_proj_c,
-      cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision, save_tape):
+      cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision, save_tape, fuse, taps):
     R, Nc, S = rays_o.shape[0], t_vals.numel(), t_vals.numel() + n_importance
     e = rays_o.new_empty
-    zf, rf = (e(R, S), e(R, S, 4)) if n_importance > 0 else (e(0), e(0))
+    want_raw = taps or not fuse
+    zf, rf = (e(R, S), (e(R, S, 4) if want_raw else e(0))) if n_importance > 0 else (e(0), e(0))
     d0 = e(R)
 
     def tape(samples):
         return rays_o.new_empty(max(ops.mlp_tape_bytes(R, samples), 16) if (save_tape and samples) else 0, dtype=torch.uint8)
 
-    return [e(R, 3), e(R), e(R), e(R), e(R, 3), e(R), e(R), e(R), e(R, Nc), zf, e(R, Nc, 4), rf, d0,
+    return [e(R, 3), e(R), e(R), e(R), e(R, 3), e(R), e(R), e(R), e(R, Nc), zf, (e(R, Nc, 4) if want_raw else e(0)), rf, d0,
             tape(Nc), tape(S if n_importance > 0 else 0)]
 
 
-_N_INPUTS = 22
+_N_INPUTS = 24
 
 
 def _setup_context(ctx, inputs, output):
     (flat_c, flat_f, packed_c, packed_f, rays_o, rays_d, near, far, t_vals, u_strat, u_fine, noise_c, noise_f, cond_proj_c,
-     cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision, save_tape) = inputs
+     cond_proj_f, cond_index, cond_rows, n_importance, white_bkgd, lindisp, precision, save_tape, fuse, taps) = inputs
     ctx.set_materialize_grads(False)          # unused outputs arrive as None: their backward branch is skipped
     rgb, disp, acc, depth, rgb0, disp0, acc0 = output[:7]
     z_c, z_f, raw_c, raw_f, depth0, tape_c, tape_f = output[8:15]
@@ -133,6 +140,7 @@ def _setup_context(ctx, inputs, output):
                           disp, acc, depth, disp0, acc0, depth0, tape_c, tape_f)
     ctx.n_importance, ctx.white_bkgd, ctx.precision, ctx.save_tape = n_importance, white_bkgd, precision, save_tape
     ctx.n_c, ctx.n_f = flat_c.numel(), flat_f.numel()
+    ctx.has_raw = taps or not fuse
 
 
 def _disp_chain(g_disp, disp, acc, depth, g_depth, g_acc):
@@ -153,6 +161,9 @@ def _backward(ctx, grads):
     (packed_c, packed_f, rays_o, rays_d, z_c, z_f, raw_c, raw_f, cond_rows, cidx, noise_c, noise_f,
      disp, acc, depth, disp0, acc0, depth0, tape_c, tape_f) = ctx.saved_tensors
     g_rgb, g_disp, g_acc, g_depth, g_rgb0, g_disp0, g_acc0, g_zstd, g_zc, g_zf, g_rawc, g_rawf = grads[:12]
+    if not ctx.has_raw:
+        raise RuntimeError("render_rays: this forward ran with compositing fused into the network query and kept no raw "
+                           "tensor (fuse_composite=True, return_taps=False); A.6 needs it -- render with fuse_composite=False")
     if g_zstd is not None or g_zc is not None or g_zf is not None:
         raise RuntimeError("render_rays: z_std / z_c / z_f are detached sample positions (SURVEY.md A.7) and carry no gradient")
     viewdirs, dnorm = ops.ray_setup(rays_d)
@@ -235,7 +246,8 @@ def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, ne
                 N_importance: int, cond: Optional[torch.Tensor] = None, *, view_id: Optional[torch.Tensor] = None,
                 u_strat: Optional[torch.Tensor] = None, u_fine: Optional[torch.Tensor] = None, raw_noise=None,
                 white_bkgd: bool = False, lindisp: bool = False, precision: str = "bf16",
-                return_taps: bool = False, save_tape: Optional[bool] = None) -> Dict[str, torch.Tensor]:
+                return_taps: bool = False, save_tape: Optional[bool] = None,
+                fuse_composite: Optional[bool] = None) -> Dict[str, torch.Tensor]:
     """Volume-render a batch of rays (A.9).
 
     rays_o, rays_d: [R,3] CUDA fp32 (rays_d un-normalised).  near/far: floats or [R]/[R,1] tensors.
@@ -247,6 +259,9 @@ def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, ne
     save_tape: record the networks' activations during the forward so that backward() skips the recompute
     (bf16 path; ~5.4 KB per sample of HBM until backward).  None = automatically, when gradients are
     being recorded for the model's parameters.
+    fuse_composite: run alpha compositing inside the bf16 network-query kernel wherever the sample
+    count allows it; without return_taps raw[R,S,4] is then never written to HBM.  None = automatically, on the
+    inference path (bf16, no tape, no gradient recorded for the parameters).
     Returns rgb[R,3], disp, acc, depth, rgb0, disp0, acc0, z_std (+ taps z_c, z_f, raw_c, raw_f, depth0).
     """
     if not rays_o.is_cuda:
@@ -303,10 +318,16 @@ def render_rays(model: NerfModel, rays_o: torch.Tensor, rays_d: torch.Tensor, ne
         save_tape = can_tape and torch.is_grad_enabled() and (model.coarse.flat.requires_grad or model.fine.flat.requires_grad)
     elif save_tape and not can_tape:
         raise ValueError("save_tape needs precision='bf16'")
+    needs_grad = torch.is_grad_enabled() and (model.coarse.flat.requires_grad or model.fine.flat.requires_grad)
+    if fuse_composite is None:
+        fuse_composite = precision == "bf16" and not save_tape and not needs_grad
+    elif fuse_composite and (precision != "bf16" or save_tape):
+        raise ValueError("fuse_composite needs precision='bf16' and no tape")
     outs = render_rays_op(model.coarse.flat, model.fine.flat, model.coarse.packed, model.fine.packed, rays_o, rays_d,
                           near_t, far_t, t_vals, u_strat, u_fine if N_importance > 0 else None, noise_c, noise_f, cpc, cpf, cidx,
                           cond if cond is not None else None, int(N_importance), bool(white_bkgd), bool(lindisp),
-                          ops.PRECISIONS[precision], bool(save_tape))
+                          ops.PRECISIONS[precision], bool(save_tape), bool(fuse_composite),
+                          bool(return_taps or needs_grad))
     n = len(_OUT_NAMES) if return_taps else 8
     return {k: v for k, v in zip(_OUT_NAMES[:n], outs[:n])}
 

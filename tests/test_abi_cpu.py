@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_sizes(lib):
-    assert lib.fnerf_abi_version() == 3
+    assert lib.fnerf_abi_version() == 4
     assert lib.fnerf_param_count(0) == 595_844
     assert lib.fnerf_param_count(1) == 595_844 + 256 * 256         # A.8
     assert lib.fnerf_packed_bytes(0) % 256 == 0 and lib.fnerf_packed_bytes(0) > 1_190_000
