@@ -41,6 +41,12 @@ constexpr int kDefaultMlpCluster = 1;     // render kernel as single CTAs (1) or
 constexpr int kStages = 3;
 constexpr int kTcThreads = 576;
 constexpr int kWorkerThreads = 512;
+#ifdef EXP_TAPE_NOAUX
+constexpr bool kTapeAux = false;          // experiment: no mask / encoding / view-layer images on the tape (timing only)
+#else
+constexpr bool kTapeAux = true;
+#endif
+constexpr int kTapeWarps = 2;             // training forward only: warps that copy finished activation images to the tape
 constexpr uint32_t kKBlockBytes = kTileM * 128;                 // 16 KB: 128 rows x 64 bf16
 constexpr uint32_t kOffAct = 0;                                 // 4 K-blocks
 constexpr uint32_t kOffPe = 4 * kKBlockBytes;                   // xyz encoding (63 -> 64), two buffers (tile parity)
@@ -119,7 +125,7 @@ template <bool kRelu, bool kSigma, bool kCond>
 __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __restrict__ walpha_s,
                                               const float* __restrict__ rowbias, uint32_t act_row_addr,
                                               uint32_t chunk0, uint32_t row, float& sigma,
-                                              uint32_t* __restrict__ mask_out = nullptr) {
+                                              uint32_t* mask_out = nullptr) {
   uint32_t v[32];
   tmem_ld32(taddr, v);
   tmem_ld_wait();
@@ -158,12 +164,10 @@ __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __res
       mask |= relu_bits(p0) << (4 * c) | relu_bits(p1) << (4 * c + 1) | relu_bits(p2) << (4 * c + 2) | relu_bits(p3) << (4 * c + 3);
     }
   }
-  if (kRelu && mask_out != nullptr) *mask_out = mask;
+  if (kRelu && mask_out != nullptr) *mask_out = mask;   // a register of the caller: stored to the tape AFTER its barrier arrival
 }
 
 __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
-// named barrier of the two worker groups (8 warps) that share an activation K-block: pair 0 = groups 0, 1; pair 1 = groups 2, 3
-__device__ __forceinline__ void pair_bar_sync(uint32_t pair) { asm volatile("bar.sync %0, 256;" ::"r"(2u + pair) : "memory"); }
 
 // kCl == 2: CTA pair (thread-block cluster of 2, tcgen05 cta_group::2).  The pair runs two 128-sample tiles in
 // lock step as ONE M = 256 MMA stream issued by the leader (cluster rank 0): every CTA keeps its own tile (A operand,
@@ -175,7 +179,8 @@ __device__ __forceinline__ void pair_bar_sync(uint32_t pair) { asm volatile("bar
 // relays "my half of stage s has landed" to the leader; tcgen05.commit multicasts stage-empty and accumulator-full to
 // both CTAs.  Both CTAs run the same number of tiles (a tile past the end is computed on clamped inputs, not stored).
 template <bool kSave, int kCl, bool kComp = false>
-__global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
+__global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThreads, 1) k_mlp_tc(const TcParams P) {
+  static_assert(!kSave || kCl == 1, "the training forward runs as single CTAs");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -190,6 +195,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   const uint32_t bar_pe = bar0 + 8u * (2 * kSt + 4);
   auto bar_acc = [&](int a) { return bar0 + 8u * (2 * kSt + 5 + a); };
   auto bar_wpeer = [&](int s) { return bar0 + 8u * (2 * kSt + 7 + s); };   // pair: the peer's half of stage s has landed
+  [[maybe_unused]] auto bar_taped = [&](int kb) { return bar0 + 8u * (3 * kSt + 7 + kb); };   // kSave: K-block kb's image has been read for the tape
+  [[maybe_unused]] const uint32_t bar_hv = bar0 + 8u * (3 * kSt + 11);                        // kSave: the view layer's output images are in K-blocks 0, 1
   const uint32_t tmem_slot = bar0 + 8u * kNumBars;
   float* heads_s = reinterpret_cast<float*>(base_ptr + kOffHeads);   // index with (kAux* - kAuxWAlpha)
 
@@ -198,10 +205,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
   // ---- one-time setup ---------------------------------------------------------------------------
   {
     const float* aux_g = reinterpret_cast<const float*>(P.packed + kSecBOffset) + kAuxWAlpha;
-    for (int i = threadIdx.x; i < kHeadFloats; i += kTcThreads) heads_s[i] = aux_g[i];
+    for (int i = threadIdx.x; i < kHeadFloats; i += blockDim.x) heads_s[i] = aux_g[i];
   }
   // constant A operand of the BIAS MMAs: ones in K rows 11 and 12 (= columns 27, 28 of a K-step-1 view), zeros elsewhere
-  for (int e = threadIdx.x; e < 128 * 16; e += kTcThreads) {
+  for (int e = threadIdx.x; e < 128 * 16; e += blockDim.x) {
     const uint32_t m = (uint32_t)e >> 4, k = (uint32_t)e & 15u;
     *reinterpret_cast<unsigned short*>(base_ptr + kOffOnes + bias_chunk_offset(m, k)) =
         (k == (uint32_t)(kBiasColHi - 16) || k == (uint32_t)(kBiasColLo - 16)) ? (unsigned short)0x3F80 : (unsigned short)0;
@@ -214,6 +221,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     mbar_init(bar_pe, 128 * kCl);                                     // xyz-encoding group (x CTAs)
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
+    if (kSave) {
+      for (int kb = 0; kb < 4; ++kb) mbar_init(bar_taped(kb), 1);
+      mbar_init(bar_hv, kWorkerThreads / 32);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -382,6 +393,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         }
       }
     }
+  } else if (kSave && warp >= 2 + kWorkerThreads / 32) {
+    // ================================ tape writers (training forward) ==============================
+    // Every finished activation K-block image (16 KB, the shared-memory bytes verbatim) goes to the tape.  Global stores
+    // stall their issuer (an SM drains ~45 B/clk into L2), so they must not be issued by the epilogue warps, whose work
+    // is on the layer-to-layer critical path: two extra warps wait for act-ready like the MMA issuer does, copy the image
+    // linearly (512 contiguous bytes per instruction) and tell the epilogue that the K-block may be overwritten.
+    const uint32_t sw = (uint32_t)warp - (2 + kWorkerThreads / 32);      // 0: K-blocks 0, 2, xyz tile;  1: K-blocks 1, 3, direction tile
+    uint32_t ph = 0;                                                      // act-ready phases consumed: one per step
+    // 16 KB image: shared memory -> tape slot, 512 contiguous bytes per instruction
+    auto copy_image = [&](uint32_t src_img, uint8_t* dst_img) {
+      const uint32_t src = src_img + ((uint32_t)lane << 4);
+      uint8_t* dstg = dst_img + ((uint32_t)lane << 4);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        uint4 t4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t4[j] = ld_shared_v4(src + (uint32_t)(b * 8 + j) * 512u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)     // streaming (evict-first) stores: the tape is next read by the backward, gigabytes later
+#ifdef EXP_TAPE_NOSTG
+          if (t4[j].x == 0x12345678u && P.M < 0)
+#endif
+          asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dstg + (b * 8 + j) * 512), "r"(t4[j].x), "r"(t4[j].y), "r"(t4[j].z), "r"(t4[j].w) : "memory");
+      }
+      __syncwarp();                      // every lane's loads have returned (their stores consumed them)
+    };
+    // A waiter must observe a barrier phase before the NEXT phase of that barrier can complete (parity waits cannot tell
+    // phases two apart).  For act-ready[kb] and the view-layer barrier that holds because the next write of the K-block
+    // waits for this warp's `taped` arrival; the encoding tiles have no such hand-shake of their own, so warp 0 copies
+    // them inside hand-shakes that do order them: the direction tile together with K-block 0 of step 0 (group 1 builds it
+    // before its first arrival on act-ready[0]), and the NEXT tile's xyz-ready phase is observed before the last `taped`
+    // arrival of this tile (the phase after it needs group 0 to get past the next tile's first epilogue).
+    if (sw == 0 && kTapeAux && n_iter > 0) mbar_wait(bar_pe, 0u);
+    for (int64_t it = 0; it < n_iter; ++it) {
+      uint8_t* tape_tile = P.tape + (size_t)tile_of(it) * kTapeFwdSlots * kKBlockBytes;
+      if (sw == 0 && kTapeAux)      // xyz tile (built a tile ahead; its buffer is rewritten two tiles later)
+        copy_image(base + kOffPe + ((uint32_t)it & 1u) * kKBlockBytes, tape_tile + (size_t)kTapeSlotPe * kKBlockBytes);
+#pragma unroll 1
+      for (int step = 0; step < 9; ++step, ++ph) {
+#pragma unroll 1
+        for (uint32_t r = 0; r < 2; ++r) {
+          const uint32_t kb = sw + 2u * r;
+          mbar_wait(bar_act(kb), ph & 1u);
+          copy_image(base + kOffAct + kb * kKBlockBytes, tape_tile + (size_t)(kTapeSlotH + 4 * step + (int)kb) * kKBlockBytes);
+          if (step == 0 && kb == 0 && kTapeAux) copy_image(base + kOffPed, tape_tile + (size_t)kTapeSlotPed * kKBlockBytes);
+          if (lane == 0) mbar_arrive(bar_taped(kb));
+        }
+      }
+      // view-layer output: the epilogue parks its two images in K-blocks 0, 1 (free once that layer's MMAs are done)
+      mbar_wait(bar_hv, (uint32_t)it & 1u);
+      copy_image(base + kOffAct + sw * kKBlockBytes, tape_tile + (size_t)(kTapeSlotHv + (int)sw) * kKBlockBytes);
+      if (sw == 0 && kTapeAux && it + 1 < n_iter) mbar_wait(bar_pe, (uint32_t)(it + 1) & 1u);
+      if (lane == 0) mbar_arrive(bar_taped(sw));
+    }
   } else {
     // ================================ workers: encodings + epilogues ===============================
     const uint32_t q = (uint32_t)warp & 3u;                 // TMEM lane quadrant this warp may read
@@ -389,6 +454,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
     const uint32_t row = q * 32u + (uint32_t)lane;
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     uint32_t acc_cnt[2] = {0u, 0u};
+    [[maybe_unused]] uint32_t tape_lo = 0, tape_hi = 0;     // kSave: images written so far into K-blocks 0/1 (ten per tile) and 2/3 (nine)
     [[maybe_unused]] uint32_t wtile = 0, wslot = 256 + grp * 64;   // tracer: 64 slots per group from 256
     const uint32_t act_row = base + kOffAct + row * 128u;
     uint8_t* ped_row_ptr = base_ptr + kOffPed + row * 128u;
@@ -417,13 +483,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         }
       }
       const uint32_t pe_row = base + kOffPe + buf * kKBlockBytes + row * 128u;
-      [[maybe_unused]] uint8_t* tape_n = kSave ? P.tape + (size_t)tile_n * kTapeFwdSlots * kKBlockBytes : nullptr;
 #pragma unroll
       for (int c16 = 0; c16 < 8; ++c16) {
         const uint4 pk = make_uint4(pack_bf16(f[c16 * 8 + 0], f[c16 * 8 + 1]), pack_bf16(f[c16 * 8 + 2], f[c16 * 8 + 3]),
                                     pack_bf16(f[c16 * 8 + 4], f[c16 * 8 + 5]), pack_bf16(f[c16 * 8 + 6], f[c16 * 8 + 7]));
         st_shared_v4(pe_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
-        if (kSave) *reinterpret_cast<uint4*>(tape_n + kTapeSlotPe * kKBlockBytes + row * 128u + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
       }
       fence_proxy_async_smem();
       if (kCl > 1) mbar_arrive_cluster(lead_bar_pe);
@@ -539,7 +603,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const uint4 pk = make_uint4(pack_bf16(d[c16 * 8 + 0], d[c16 * 8 + 1]), pack_bf16(d[c16 * 8 + 2], d[c16 * 8 + 3]),
                                       pack_bf16(d[c16 * 8 + 4], d[c16 * 8 + 5]), pack_bf16(d[c16 * 8 + 6], d[c16 * 8 + 7]));
           st_shared_v4(ped_row + (((uint32_t)c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
-          if (kSave) *reinterpret_cast<uint4*>(tape_tile + kTapeSlotPed * kKBlockBytes + row * 128u + (((uint32_t)c16 ^ (row & 7u)) << 4)) = pk;
         }
         fence_proxy_async_smem();
       }
@@ -566,8 +629,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           const uint32_t kb = unit >> 1, half = unit & 1u;
           const uint32_t col0 = unit * 32u;
           const uint32_t dst = act_row + kb * kKBlockBytes;
-          uint32_t* sv = kSave ? mask_row + (step * 8 + (int)unit) * 128 : nullptr;   // ReLU bitmask word (steps 0..7)
-          if (kSave) pair_bar_sync(grp >> 1);          // the pair's read-back of this K-block's previous image is done
+          // ReLU bitmask word (steps 0..7).  Stored after the act-ready arrival below: the arrival's release (and the
+          // proxy fence) wait for the thread's outstanding global stores, an L2 round trip on the layer-to-layer critical path
+          uint32_t mask_word = 0u;
+          uint32_t* sv = (kSave && kTapeAux) ? &mask_word : nullptr;
+#ifndef EXP_TAPE_NOWAIT
+          if (kSave) mbar_wait(bar_taped(kb), ((round ? tape_hi : tape_lo) & 1u) ^ 1u);
+#endif   // the tape writers have read this K-block's previous image
           if (step == 8)
             epilogue_unit<false, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma, sv);
           else if (step == 7)
@@ -585,26 +653,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
             if (kCl > 1) mbar_arrive_cluster(lead_bar_act0 + 8u * kb);
             else mbar_arrive(bar_act(kb));
           }
-          if (kSave) {
-            // Training tape: the 16 KB image of K-block kb is complete once the two groups that share it have
-            // stored their halves.  Those 8 warps then copy it to the tape LINEARLY (2 KB per warp, 512
-            // contiguous bytes per instruction) -- a row-per-thread store of the same bytes touches 32 lines per
-            // instruction.  The same 8 warps overwrite this K-block at the next step, after the pair barrier
-            // above their stores, so the read-back never races a writer.
-            pair_bar_sync(grp >> 1);
-            const uint32_t off = (((grp & 1u) * 4u + q) << 11) + ((uint32_t)lane << 4);
-            const uint32_t src = base + kOffAct + kb * kKBlockBytes + off;
-            uint8_t* dstg = tape_tile + (size_t)(kTapeSlotH + 4 * step + (int)kb) * kKBlockBytes + off;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {       // streaming (evict-first) stores: the tape is next read by wgrad, gigabytes later
-              const uint4 t4 = ld_shared_v4(src + i * 512);
-              asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dstg + i * 512), "r"(t4.x), "r"(t4.y), "r"(t4.z), "r"(t4.w) : "memory");
-            }
-          }
+          if (kSave && kTapeAux && step < 8) mask_row[(step * 8 + (int)unit) * 128] = mask_word;
           FN_TRACE(wtile == 2 && row == 0, wslot++);
         }
         // next tile's xyz encodings, in the shadow of layer 1's MMAs (the buffer's last reader, layer 5 of the tile
         // before this one, completed long ago)
+        ++tape_lo; ++tape_hi;
         if (step == 0 && grp == 0 && it + 1 < n_iter) compute_pe(tile_of(it + 1), (uint32_t)((it + 1) & 1));
         if (kComp && grp == 3 && step < 3 && it > 0) comp_phase(step + 1);
       }
@@ -626,20 +680,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
           c1 = fmaf(h, wrgb[kWV + col], c1);
           c2 = fmaf(h, wrgb[2 * kWV + col], c2);
         }
-        if (kSave) {             // HV image: 2 K-blocks of 64 columns; this group's 32 columns = 4 chunks of its row
-          uint8_t* hv_row = tape_tile + (size_t)(kTapeSlotHv + (int)(grp >> 1)) * kKBlockBytes + row * 128u;
-          uint32_t mask = 0u;
+        [[maybe_unused]] uint32_t hv_mask = 0u;
+        if (kSave) {
+          // view-layer output for the tape: 2 images of 64 columns, parked in K-blocks 0 / 1 (their last readers, this
+          // layer's MMAs, are complete) in the layout of every other activation image; the tape writers copy them out
+          const uint32_t kb = grp >> 1;
+          mbar_wait(bar_taped(kb), (tape_lo & 1u) ^ 1u);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint4 pk = make_uint4(pack_bf16_relu(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])),
                                         pack_bf16_relu(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])),
                                         pack_bf16_relu(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])),
                                         pack_bf16_relu(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])));
-            mask |= relu_bits(pk.x) << (4 * c) | relu_bits(pk.y) << (4 * c + 1) | relu_bits(pk.z) << (4 * c + 2) | relu_bits(pk.w) << (4 * c + 3);
+            hv_mask |= relu_bits(pk.x) << (4 * c) | relu_bits(pk.y) << (4 * c + 1) | relu_bits(pk.z) << (4 * c + 2) | relu_bits(pk.w) << (4 * c + 3);
             const uint32_t c16 = (grp & 1u) * 4u + (uint32_t)c;
-            *reinterpret_cast<uint4*>(hv_row + ((c16 ^ (row & 7u)) << 4)) = pk;
+            st_shared_v4(act_row + kb * kKBlockBytes + ((c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
           }
-          mask_row[(kMaskUnitHv + (int)grp) * 128] = mask;
+          ++tape_lo;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_hv);
         }
         tc_fence_before();
         // The partials of three groups park in logical chunks 5..7 of this row of the direction tile (its unused upper
@@ -650,6 +710,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_mlp_tc(const TcParams P) {
         const uint32_t park = grp == 0 ? kFin : grp;          // group 0 parks in the finishing group's chunk when it is not the finisher
         if (grp != kFin) *reinterpret_cast<float4*>(ped_row_ptr + (((4u + park) ^ (row & 7u)) << 4)) = make_float4(c0, c1, c2, sigma);
         worker_bar_sync();
+        if (kSave && kTapeAux) mask_row[(kMaskUnitHv + (int)grp) * 128] = hv_mask;
         if (grp == kFin) {
           // chunks 5, 6 hold groups 1, 2; chunk 7 holds group 3 (plain kernel) or group 0 (kComp).  The sum is always
           // (g0 + g1) + (g2 + g3): fp32 addition commutes, so both kernels produce the same bits
@@ -767,7 +828,7 @@ int launch_mlp_tc_tape(const MlpArgs& a, uint8_t* tape, uint32_t* mask_tape, cud
   }
   int64_t blocks = num_sms();
   if (blocks > P.ntiles) blocks = P.ntiles;
-  if (sv) k_mlp_tc<true, 1><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
+  if (sv) k_mlp_tc<true, 1><<<(unsigned)blocks, kTcThreads + 32 * kTapeWarps, kTcSmemBytes, s>>>(P);
   else k_mlp_tc<false, 1><<<(unsigned)blocks, kTcThreads, kTcSmemBytes, s>>>(P);
   return check_launch("mlp_tc");
 }
