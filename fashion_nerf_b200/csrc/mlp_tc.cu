@@ -13,6 +13,10 @@
 //               all groups run the per-layer epilogue in 32-column units: tcgen05.ld -> ReLU -> bf16
 //               -> swizzled st.shared as the next layer's A operand.  Group g converts units g and
 //               g+4 of the 8 units of a layer.
+//   warps 18,19 training forward only (kSave, 640 threads): tape writers -- copy every finished 16 KB activation /
+//               encoding image from shared memory to the HBM tape, so that no epilogue warp ever issues a global store
+//               ahead of a barrier arrival (the arrival's release waits for the thread's outstanding stores).
+// kComp (inference): alpha compositing (A.5) runs in the finishing group, deferred into the next tile (comp_phase).
 // The epilogue hands the activation tile over in 64-column K-blocks (one mbarrier each, two units),
 // so the next layer's MMAs on K-blocks 0/1 start while K-blocks 2/3 are still being converted; the
 // two TMEM accumulators make that overlap legal.

@@ -5,7 +5,7 @@
 
 namespace fnerf {
 
-// one CTA per chunk
+// grid (chunk, quarter of the chunk's elements): 48 CTAs alone left most of the chip idle for 36 us per re-pack
 __global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict__ packed, int cond) {
   const int c = blockIdx.x;
   const ChunkDesc cd = chunk_desc(c);
@@ -14,7 +14,7 @@ __global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict_
   const float* bvec = flat + flat_bias_offset(cd.layer, cond);
   uint8_t* dst = packed + chunk_offset(c);
   if (cd.kind == CHUNK_BIAS) {                            // MN-major K = 16 tile: K rows 11 / 12 = bias hi / lo
-    for (int e = threadIdx.x; e < 256 * 16; e += blockDim.x) {
+    for (int e = blockIdx.y * 1024 + threadIdx.x; e < (blockIdx.y + 1) * 1024; e += blockDim.x) {
       const int n = e >> 4, k = e & 15;
       const float b = bvec[n];
       const float hi = __bfloat162float(__float2bfloat16_rn(b));
@@ -24,7 +24,7 @@ __global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict_
     return;
   }
   const int rows = c >= kFirstViewChunk ? 128 : 256;
-  for (int e = threadIdx.x; e < rows * 64; e += blockDim.x) {
+  for (int e = blockIdx.y * rows * 16 + threadIdx.x; e < (blockIdx.y + 1) * rows * 16; e += blockDim.x) {
     const int r = e >> 6, k = e & 63;                     // output feature r, K column k of the chunk
     float v = 0.0f;
     if (cd.kind == CHUNK_TRUNK) {
@@ -115,7 +115,7 @@ __global__ void k_unpack(const uint8_t* __restrict__ packed, float* __restrict__
 
 int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s) {
   uint8_t* p = reinterpret_cast<uint8_t*>(packed);
-  k_pack_bf16<<<kNumChunks, 256, 0, s>>>(flat, p, cond);
+  k_pack_bf16<<<dim3(kNumChunks, 4), 256, 0, s>>>(flat, p, cond);
   k_pack_aux<<<(kAuxFloats + 255) / 256, 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecBOffset), cond);
   int64_t nmax = 0;
   for (int j = 0; j < 10; ++j) {
