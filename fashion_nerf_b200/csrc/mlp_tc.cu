@@ -130,9 +130,15 @@ __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __res
                                               const float* __restrict__ rowbias, uint32_t act_row_addr,
                                               uint32_t chunk0, uint32_t row, float& sigma,
                                               uint32_t* mask_out = nullptr) {
+#ifdef EXP_NOEPI
+  return;      // experiment: how fast is the kernel when the epilogue costs nothing (results are garbage)
+#endif
   uint32_t v[32];
   tmem_ld32(taddr, v);
   tmem_ld_wait();
+#ifdef EXP_LDONLY
+  if (v[0] != 0x12345678u) return;   // experiment: TMEM read-out only
+#endif
   uint32_t mask = 0u;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {            // 16-byte chunk = 8 columns
