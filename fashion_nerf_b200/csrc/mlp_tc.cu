@@ -413,6 +413,17 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
     uint32_t ph = 0;                                                      // act-ready phases consumed: one per step
     // 16 KB image: shared memory -> tape slot, 512 contiguous bytes per instruction
     auto copy_image = [&](uint32_t src_img, uint8_t* dst_img) {
+#ifdef EXP_TAPE_BULK
+      // experiment: one bulk-TMA store per image (the writers fenced their stores for the async proxy); returns once the
+      // engine has READ the image
+      if (lane == 0) {
+        bulk_s2g(dst_img, src_img, kKBlockBytes);
+        bulk_commit();
+        bulk_wait_read<0>();
+      }
+      __syncwarp();
+      return;
+#endif
       const uint32_t src = src_img + ((uint32_t)lane << 4);
       uint8_t* dstg = dst_img + ((uint32_t)lane << 4);
 #pragma unroll

@@ -5,16 +5,18 @@
 
 namespace fnerf {
 
-// grid (chunk, quarter of the chunk's elements): 48 CTAs alone left most of the chip idle for 36 us per re-pack
-__global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict__ packed, int cond) {
-  const int c = blockIdx.x;
+// The four sections of the blob are written by ONE launch (k_pack_all): a re-pack follows every optimiser step, and four
+// launches per network were 2 % of a training step.  Each section keeps its own block decomposition (bx, by).
+// section A, blocks (chunk, quarter of the chunk's elements): 48 CTAs alone left most of the chip idle for 36 us per re-pack
+__device__ __forceinline__ void pack_bf16_block(const float* __restrict__ flat, uint8_t* __restrict__ packed, int cond, int bx, int by) {
+  const int c = bx;
   const ChunkDesc cd = chunk_desc(c);
   const LayerDim d = layer_dim(cd.layer, cond);
   const float* W = flat + flat_weight_offset(cd.layer, cond);
   const float* bvec = flat + flat_bias_offset(cd.layer, cond);
   uint8_t* dst = packed + chunk_offset(c);
   if (cd.kind == CHUNK_BIAS) {                            // MN-major K = 16 tile: K rows 11 / 12 = bias hi / lo
-    for (int e = blockIdx.y * 1024 + threadIdx.x; e < (blockIdx.y + 1) * 1024; e += blockDim.x) {
+    for (int e = by * 1024 + threadIdx.x; e < (by + 1) * 1024; e += blockDim.x) {
       const int n = e >> 4, k = e & 15;
       const float b = bvec[n];
       const float hi = __bfloat162float(__float2bfloat16_rn(b));
@@ -24,7 +26,7 @@ __global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict_
     return;
   }
   const int rows = c >= kFirstViewChunk ? 128 : 256;
-  for (int e = blockIdx.y * rows * 16 + threadIdx.x; e < (blockIdx.y + 1) * rows * 16; e += blockDim.x) {
+  for (int e = by * rows * 16 + threadIdx.x; e < (by + 1) * rows * 16; e += blockDim.x) {
     const int r = e >> 6, k = e & 63;                     // output feature r, K column k of the chunk
     float v = 0.0f;
     if (cd.kind == CHUNK_TRUNK) {
@@ -44,13 +46,13 @@ __global__ void k_pack_bf16(const float* __restrict__ flat, uint8_t* __restrict_
 }
 
 // Section E: transposed chunks for dgrad: chunk row k = input feature, column j = output feature 64*kb + j
-__global__ void k_pack_bf16_T(const float* __restrict__ flat, uint8_t* __restrict__ secE, int cond) {
-  const int c = blockIdx.x;
+__device__ __forceinline__ void pack_bf16_T_block(const float* __restrict__ flat, uint8_t* __restrict__ secE, int cond, int bx, int by) {
+  const int c = bx;
   const ChunkTDesc cd = chunk_t_desc(c);
   const LayerDim d = layer_dim(cd.layer, cond);
   const float* W = flat + flat_weight_offset(cd.layer, cond);
   const int base = (cd.layer == 5) ? kPE + (cond ? kCond : 0) : 0;
-  for (int e = blockIdx.y * 4096 + threadIdx.x; e < (blockIdx.y + 1) * 4096; e += blockDim.x) {   // grid.y = 4 quarters of the chunk
+  for (int e = by * 4096 + threadIdx.x; e < (by + 1) * 4096; e += blockDim.x) {   // by = quarter of the chunk
     const int k = e >> 6, j = e & 63;
     const int n = cd.kb * 64 + j;
     const float v = W[(int64_t)n * d.in + base + k];
@@ -58,8 +60,8 @@ __global__ void k_pack_bf16_T(const float* __restrict__ flat, uint8_t* __restric
   }
 }
 
-__global__ void k_pack_aux(const float* __restrict__ flat, float* __restrict__ aux, int cond) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_aux_block(const float* __restrict__ flat, float* __restrict__ aux, int cond, int bx) {
+  int i = bx * blockDim.x + threadIdx.x;
   if (i >= kAuxFloats) return;
   float v = 0.0f;
   if (i < kAuxBiasFeat) v = flat[flat_bias_offset(i >> 8, cond) + (i & 255)];
@@ -73,11 +75,11 @@ __global__ void k_pack_aux(const float* __restrict__ flat, float* __restrict__ a
 }
 
 // Section C: layer j stored K-major: wt[k][n] = W[n][k]
-__global__ void k_pack_simt(const float* __restrict__ flat, float* __restrict__ secC, int cond) {
-  const int j = blockIdx.y;                      // one grid row per fp32 layer
+__device__ __forceinline__ void pack_simt_block(const float* __restrict__ flat, float* __restrict__ secC, int cond, int bx, int by) {
+  const int j = by;                              // one row of blocks per fp32 layer
   const int l = simt_layer_id(j);
   const LayerDim d = layer_dim(l, cond);
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t e = (int64_t)bx * blockDim.x + threadIdx.x;
   if (e >= (int64_t)d.out * d.in) return;
   const int k = (int)(e / d.out), n = (int)(e % d.out);
   secC[simt_offset_floats(j, cond) + e] = flat[flat_weight_offset(l, cond) + (int64_t)n * d.in + k];
@@ -113,18 +115,28 @@ __global__ void k_unpack(const uint8_t* __restrict__ packed, float* __restrict__
   flat[e] = v;
 }
 
+constexpr int kPackBlocksA = kNumChunks * 4, kPackBlocksAux = (kAuxFloats + 255) / 256, kPackBlocksT = kNumChunksT * 4;
+__global__ void __launch_bounds__(256) k_pack_all(const float* __restrict__ flat, uint8_t* __restrict__ p, int cond, int simt_bx) {
+  int b = (int)blockIdx.x;
+  if (b < kPackBlocksA) return pack_bf16_block(flat, p, cond, b >> 2, b & 3);
+  b -= kPackBlocksA;
+  if (b < kPackBlocksT) return pack_bf16_T_block(flat, p + sec_e_offset(cond), cond, b >> 2, b & 3);
+  b -= kPackBlocksT;
+  if (b < kPackBlocksAux) return pack_aux_block(flat, reinterpret_cast<float*>(p + kSecBOffset), cond, b);
+  b -= kPackBlocksAux;
+  pack_simt_block(flat, reinterpret_cast<float*>(p + kSecCOffset), cond, b % simt_bx, b / simt_bx);
+}
+
 int launch_pack(const float* flat, void* packed, int cond, cudaStream_t s) {
   uint8_t* p = reinterpret_cast<uint8_t*>(packed);
-  k_pack_bf16<<<dim3(kNumChunks, 4), 256, 0, s>>>(flat, p, cond);
-  k_pack_aux<<<(kAuxFloats + 255) / 256, 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecBOffset), cond);
   int64_t nmax = 0;
   for (int j = 0; j < 10; ++j) {
     const LayerDim d = layer_dim(simt_layer_id(j), cond);
     if ((int64_t)d.out * d.in > nmax) nmax = (int64_t)d.out * d.in;
   }
-  k_pack_simt<<<dim3((unsigned)((nmax + 255) / 256), 10), 256, 0, s>>>(flat, reinterpret_cast<float*>(p + kSecCOffset), cond);
-  k_pack_bf16_T<<<dim3(kNumChunksT, 4), 256, 0, s>>>(flat, p + sec_e_offset(cond), cond);
-  return check_launch("pack_weights", 4);
+  const int simt_bx = (int)((nmax + 255) / 256);
+  k_pack_all<<<kPackBlocksA + kPackBlocksT + kPackBlocksAux + simt_bx * 10, 256, 0, s>>>(flat, p, cond, simt_bx);
+  return check_launch("pack_weights");
 }
 
 int launch_unpack(const void* packed, float* flat, int cond, cudaStream_t s) {

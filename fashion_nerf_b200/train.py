@@ -118,8 +118,9 @@ class Trainer:
         try:
             out = render_rays(m, rays_o, rays_d, near, far, N_samples, N_importance, cond, view_id=view_id,
                               u_strat=u_strat, u_fine=u_fine, white_bkgd=white_bkgd, precision=precision)
-            loss_f = ((out["rgb"] - target) ** 2).mean()
-            loss = loss_f + ((out["rgb0"] - target) ** 2).mean() if N_importance > 0 else loss_f
+            mse = torch.nn.functional.mse_loss                   # one fused kernel each way instead of sub / pow / mean / ...
+            loss_f = mse(out["rgb"], target)
+            loss = loss_f + mse(out["rgb0"], target) if N_importance > 0 else loss_f
             loss.backward()
         finally:                                  # never leave autograd leaves behind in the model
             m.coarse.flat, m.fine.flat = fc.detach(), ff.detach()
