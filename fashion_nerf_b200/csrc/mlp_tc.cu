@@ -10,15 +10,15 @@
 //               D = one of two 128x256 fp32 accumulators in TMEM (layer parity);
 //   warps 2..17 workers, four groups of four warps (a warp's TMEM lane quadrant is warp%4, so each
 //               group covers the 128 rows): group 0 / 1 build the xyz / direction encoding tiles;
-//               all groups run the per-layer epilogue in 32-column units: tcgen05.ld -> ReLU -> bf16
-//               -> swizzled st.shared as the next layer's A operand.  Group g converts units g and
-//               g+4 of the 8 units of a layer.
+//               all groups run the per-layer epilogue in 16-column pieces: tcgen05.ld -> ReLU -> bf16
+//               -> swizzled st.shared as the next layer's A operand.  In round kb (0..3) group g converts
+//               columns 16g..16g+15 of K-block kb, so all 16 warps finish K-block 0 first.
 //   warps 18,19 training forward only (kSave, 640 threads): tape writers -- copy every finished 16 KB activation /
 //               encoding image from shared memory to the HBM tape, so that no epilogue warp ever issues a global store
 //               ahead of a barrier arrival (the arrival's release waits for the thread's outstanding stores).
 // kComp (inference): alpha compositing (A.5) runs in the finishing group, deferred into the next tile (comp_phase).
-// The epilogue hands the activation tile over in 64-column K-blocks (one mbarrier each, two units),
-// so the next layer's MMAs on K-blocks 0/1 start while K-blocks 2/3 are still being converted; the
+// The epilogue hands the activation tile over in 64-column K-blocks (one mbarrier each, 16 arrivals),
+// so the next layer's MMAs on K-block 0 start while K-blocks 1..3 are still being converted; the
 // two TMEM accumulators make that overlap legal.
 //
 // Biases ride in the GEMM: the direction-encoding tile carries 1.0 in its two spare columns (27, 28)
@@ -122,26 +122,25 @@ struct TcParams {
 // non-negative bf16 (<= 0x7F80) sets bit 15 exactly when it is non-zero and never carries into the other half
 __device__ __forceinline__ uint32_t relu_bits(uint32_t packed) { return ((packed + 0x7FFF7FFFu) >> 15) & 0x00010001u; }
 
-// epilogue of one 32-column unit: TMEM -> (+rowbias) -> [ReLU] -> bf16 -> swizzled smem.  The layer
-// bias is already in the accumulator.  `chunk0` is the index (0 or 4) of the unit's first 16-byte
-// chunk inside its 128-byte K-block row.
+// epilogue of one 16-column piece (two 16-byte chunks of a K-block row): TMEM -> (+rowbias) -> [ReLU] -> bf16 -> swizzled
+// smem.  The layer bias is already in the accumulator.  `chunk0` is the index (0, 2, 4, 6) of the piece's first 16-byte
+// chunk inside its 128-byte K-block row.  Returns the ReLU bits of the piece (training tape): bit j = column 2j > 0,
+// bit 16 + j = column 2j + 1 > 0, j = 0..7.
 template <bool kRelu, bool kSigma, bool kCond>
-__device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __restrict__ walpha_s,
-                                              const float* __restrict__ rowbias, uint32_t act_row_addr,
-                                              uint32_t chunk0, uint32_t row, float& sigma,
-                                              uint32_t* mask_out = nullptr) {
+__device__ __forceinline__ uint32_t epilogue_piece(uint32_t taddr, const float* __restrict__ walpha_s, const float* __restrict__ rowbias,
+                                                   uint32_t act_row_addr, uint32_t chunk0, uint32_t row, float& sigma) {
 #ifdef EXP_NOEPI
-  return;      // experiment: how fast is the kernel when the epilogue costs nothing (results are garbage)
+  return 0u;   // experiment: how fast is the kernel when the epilogue costs nothing (results are garbage)
 #endif
-  uint32_t v[32];
-  tmem_ld32(taddr, v);
+  uint32_t v[16];
+  tmem_ld16(taddr, v);
   tmem_ld_wait();
 #ifdef EXP_LDONLY
-  if (v[0] != 0x12345678u) return;   // experiment: TMEM read-out only
+  if (v[0] != 0x12345678u) return 0u;   // experiment: TMEM read-out only
 #endif
   uint32_t mask = 0u;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {            // 16-byte chunk = 8 columns
+  for (int c = 0; c < 2; ++c) {
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[c * 8 + j]);
@@ -170,11 +169,9 @@ __device__ __forceinline__ void epilogue_unit(uint32_t taddr, const float* __res
     }
     const uint32_t c16 = chunk0 + (uint32_t)c;
     st_shared_v4(act_row_addr + ((c16 ^ (row & 7u)) << 4), p0, p1, p2, p3);
-    if (kRelu && mask_out != nullptr) {   // training tape: bit i = column 2i > 0, bit 16+i = column 2i+1 > 0
-      mask |= relu_bits(p0) << (4 * c) | relu_bits(p1) << (4 * c + 1) | relu_bits(p2) << (4 * c + 2) | relu_bits(p3) << (4 * c + 3);
-    }
+    if (kRelu) mask |= relu_bits(p0) << (4 * c) | relu_bits(p1) << (4 * c + 1) | relu_bits(p2) << (4 * c + 2) | relu_bits(p3) << (4 * c + 3);
   }
-  if (kRelu && mask_out != nullptr) *mask_out = mask;   // a register of the caller: stored to the tape AFTER its barrier arrival
+  return mask;
 }
 
 __device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
@@ -227,7 +224,8 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSt; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); mbar_init(bar_wpeer(s), 1); }
-    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 8 * kCl);   // one arrive per warp: 2 groups x 4 warps per K-block (x CTAs)
+    // one arrive per warp: every K-block is handed over by all 16 worker warps (16-column pieces; x CTAs)
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_act(kb), 16 * kCl);
     mbar_init(bar_pe, 128 * kCl);                                     // xyz-encoding group (x CTAs)
     mbar_init(bar_acc(0), 1);
     mbar_init(bar_acc(1), 1);
@@ -360,16 +358,6 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
           }
           tc_fence_after();
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
-          // probe the next chunk's barriers now; the answers are needed only after this chunk is issued
-          const uint32_t act_next = act_cnt + ((op.gated && op.kb == 3) ? 1u : 0u);
-          w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full((wc + 1) % kSt), ((wc + 1) / kSt) & 1u) &&
-                                                (kCl == 1 || mbar_test_wait(bar_wpeer((wc + 1) % kSt), ((wc + 1) / kSt) & 1u)));
-          if (c + 1 < kNumChunks) {
-            const MmaChunk nx = mma_chunk(c + 1);
-            a_ready = nx.gated ? __all_sync(0xffffffffu, mbar_test_wait(bar_act(nx.kb), act_next & 1u)) : true;
-          } else {
-            a_ready = true;
-          }
           const uint64_t a_desc = op.a_sel == 3 ? desc_ones
                                   : (op.a_sel == 0 ? desc_act + (uint64_t)(op.kb * (kKBlockBytes >> 4))
                                                    : (op.a_sel == 1 ? desc_pe + (uint64_t)((tile_cnt & 1u) * (kKBlockBytes >> 4)) : desc_ped)) +
@@ -397,6 +385,17 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
             }
           }
           __syncwarp();
+          // probe the next chunk's barriers AFTER this chunk's MMAs are in the queue: the probes (two test_wait round trips and
+          // two votes) cost ~100 cycles that used to sit between an act-ready wake-up and the first MMA of the chunk
+          const uint32_t act_next = act_cnt + ((op.gated && op.kb == 3) ? 1u : 0u);
+          w_ready = __all_sync(0xffffffffu, mbar_test_wait(bar_full((wc + 1) % kSt), ((wc + 1) / kSt) & 1u) &&
+                                                (kCl == 1 || mbar_test_wait(bar_wpeer((wc + 1) % kSt), ((wc + 1) / kSt) & 1u)));
+          if (c + 1 < kNumChunks) {
+            const MmaChunk nx = mma_chunk(c + 1);
+            a_ready = nx.gated ? __all_sync(0xffffffffu, mbar_test_wait(bar_act(nx.kb), act_next & 1u)) : true;
+          } else {
+            a_ready = true;
+          }
           FN_TRACE(tile_cnt == 2 && lane == 0, tslot++);
           act_cnt = act_next;
           ++wc;
@@ -475,7 +474,6 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
     const uint32_t row = q * 32u + (uint32_t)lane;
     const uint32_t tmem_row = tmem_base + ((q * 32u) << 16);
     uint32_t acc_cnt[2] = {0u, 0u};
-    [[maybe_unused]] uint32_t tape_lo = 0, tape_hi = 0;     // kSave: images written so far into K-blocks 0/1 (ten per tile) and 2/3 (nine)
     [[maybe_unused]] uint32_t wtile = 0, wslot = 256 + grp * 64;   // tracer: 64 slots per group from 256
     const uint32_t act_row = base + kOffAct + row * 128u;
     uint8_t* ped_row_ptr = base_ptr + kOffPed + row * 128u;
@@ -644,27 +642,26 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
         ++acc_cnt[a];
         tc_fence_after();
         const uint32_t tacc = tmem_row + (uint32_t)a * 256u;
+        // K-block kb of the next layer's A operand is produced in round kb by ALL 16 warps (group g: its columns
+        // 16g..16g+15): the first K-block is complete after a quarter of the layer's epilogue instead of half of it, and
+        // the issuer's wait for it is the longest stall of a layer (timeline: ~1000 of ~3250 cycles).
+        [[maybe_unused]] uint32_t mask_a = 0u, mask_b = 0u;   // training tape: ReLU bits of the pieces of K-blocks 0, 1 / 2, 3
 #pragma unroll 1
-        for (int round = 0; round < 2; ++round) {
-          const uint32_t unit = grp + 4u * (uint32_t)round;  // 32-column unit 0..7
-          const uint32_t kb = unit >> 1, half = unit & 1u;
-          const uint32_t col0 = unit * 32u;
+        for (uint32_t kb = 0; kb < 4; ++kb) {
+          const uint32_t col0 = kb * 64u + grp * 16u;
           const uint32_t dst = act_row + kb * kKBlockBytes;
-          // ReLU bitmask word (steps 0..7).  Stored after the act-ready arrival below: the arrival's release (and the
-          // proxy fence) wait for the thread's outstanding global stores, an L2 round trip on the layer-to-layer critical path
-          uint32_t mask_word = 0u;
-          uint32_t* sv = (kSave && kTapeAux) ? &mask_word : nullptr;
-#ifndef EXP_TAPE_NOWAIT
-          if (kSave) mbar_wait(bar_taped(kb), ((round ? tape_hi : tape_lo) & 1u) ^ 1u);
-#endif   // the tape writers have read this K-block's previous image
+          // training forward: the tape writers have read this K-block's previous image (K-blocks 0 / 1 carry ten images
+          // per tile -- nine layers and the view layer's output --, K-blocks 2 / 3 nine)
+          if (kSave) mbar_wait(bar_taped(kb), (((kb < 2 ? 10u : 9u) * (uint32_t)it + (uint32_t)step) & 1u) ^ 1u);
+          uint32_t mbits;
           if (step == 8)
-            epilogue_unit<false, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma, sv);
+            mbits = epilogue_piece<false, false, false>(tacc + col0, nullptr, nullptr, dst, grp * 2u, row, sigma);
           else if (step == 7)
-            epilogue_unit<true, true, false>(tacc + col0, heads_s + col0, nullptr, dst, half * 4u, row, sigma, sv);
+            mbits = epilogue_piece<true, true, false>(tacc + col0, heads_s + col0, nullptr, dst, grp * 2u, row, sigma);
           else if (step == 5 && P.cond)
-            epilogue_unit<true, false, true>(tacc + col0, nullptr, rowbias + col0, dst, half * 4u, row, sigma, sv);
+            mbits = epilogue_piece<true, false, true>(tacc + col0, nullptr, rowbias + col0, dst, grp * 2u, row, sigma);
           else
-            epilogue_unit<true, false, false>(tacc + col0, nullptr, nullptr, dst, half * 4u, row, sigma, sv);
+            mbits = epilogue_piece<true, false, false>(tacc + col0, nullptr, nullptr, dst, grp * 2u, row, sigma);
           // every lane publishes its own stores to the async proxy; one lane per warp then arrives
           // (512 per-thread arrives on two barriers cost ~10 % of the epilogue in SYNCS throttling)
           fence_proxy_async_smem();
@@ -674,12 +671,21 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
             if (kCl > 1) mbar_arrive_cluster(lead_bar_act0 + 8u * kb);
             else mbar_arrive(bar_act(kb));
           }
-          if (kSave && kTapeAux && step < 8) mask_row[(step * 8 + (int)unit) * 128] = mask_word;
-          FN_TRACE(wtile == 2 && row == 0, wslot++);
+          if (kSave) { if (kb < 2) mask_a |= mbits << (8u * kb); else mask_b |= mbits << (8u * (kb - 2u)); }
+          FN_TRACE(wtile == 2 && row == 0 && (kb & 1u), wslot++);
+        }
+        if (kSave && kTapeAux && step < 8) {
+          // ReLU bits of piece (kb, grp) = bytes h and 2 + h (h = grp & 1) of the mask word of 32-column unit 2 kb + grp / 2.
+          // All eight bytes are stored after the step's LAST act-ready arrival: an arrival's release (and the proxy fence)
+          // wait for the thread's outstanding global stores -- an L2 round trip on the layer-to-layer critical path
+          uint8_t* mw = reinterpret_cast<uint8_t*>(mask_row + (step * 8 + (int)(grp >> 1)) * 128) + (grp & 1u);
+          mw[0] = (uint8_t)mask_a;                     mw[2] = (uint8_t)(mask_a >> 16);          // K-block 0: unit 0 / 1
+          mw[2 * 512] = (uint8_t)(mask_a >> 8);        mw[2 * 512 + 2] = (uint8_t)(mask_a >> 24); // K-block 1: unit 2 / 3
+          mw[4 * 512] = (uint8_t)mask_b;               mw[4 * 512 + 2] = (uint8_t)(mask_b >> 16);
+          mw[6 * 512] = (uint8_t)(mask_b >> 8);        mw[6 * 512 + 2] = (uint8_t)(mask_b >> 24);
         }
         // next tile's xyz encodings, in the shadow of layer 1's MMAs (the buffer's last reader, layer 5 of the tile
         // before this one, completed long ago)
-        ++tape_lo; ++tape_hi;
         if (step == 0 && grp == 0 && it + 1 < n_iter) compute_pe(tile_of(it + 1), (uint32_t)((it + 1) & 1));
         if (kComp && grp == 3 && step < 3 && it > 0) comp_phase(step + 1);
       }
@@ -706,7 +712,7 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
           // view-layer output for the tape: 2 images of 64 columns, parked in K-blocks 0 / 1 (their last readers, this
           // layer's MMAs, are complete) in the layout of every other activation image; the tape writers copy them out
           const uint32_t kb = grp >> 1;
-          mbar_wait(bar_taped(kb), (tape_lo & 1u) ^ 1u);
+          mbar_wait(bar_taped(kb), ((10u * (uint32_t)it + 9u) & 1u) ^ 1u);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint4 pk = make_uint4(pack_bf16_relu(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])),
@@ -717,7 +723,6 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
             const uint32_t c16 = (grp & 1u) * 4u + (uint32_t)c;
             st_shared_v4(act_row + kb * kKBlockBytes + ((c16 ^ (row & 7u)) << 4), pk.x, pk.y, pk.z, pk.w);
           }
-          ++tape_lo;
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_hv);

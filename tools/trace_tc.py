@@ -9,7 +9,8 @@ OUT = os.path.join(ROOT, "fashion_nerf_b200", "libfnerf_trace.so")
 
 
 def build(extra=(), out=None):
-    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "sampling.cu", "composite.cu", "pack.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_bwd.cu")]
+    from fashion_nerf_b200._build import SOURCES
+    srcs = [os.path.join(CSRC, f) for f in SOURCES]
     cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DFNERF_TRACE", *extra,
            "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-shared", "-o", out or OUT, *srcs, "-lcudart"]
     subprocess.run(cmd, check=True)
