@@ -50,8 +50,11 @@ GRAD_BYTES = 4_766_752               # 1,191,688 fp32 gradients all-reduced per 
 # dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass k_mlp_tc launch of THIS workload (640,000 rays x 192
 # samples) from one `ncu --set full` capture of `bench.py --steps 1 --warmup 3`; a STATIC figure copied from profiles/
 # (the driver's run is not under ncu), next to the algorithmic 20 B/sample = 2,457,600,000
-NCU_FINE_LAUNCH_DRAM_BYTES = 542_652_160 + 1_917_181_000
-NCU_TRAFFIC_SOURCE = "static, from profiles/r1_bench_fine_launch_ncu_key_metrics.txt (dram read + write of this launch, ncu --set full); not measured in this run"
+# dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass launch of this very workload, from the tracked ncu --set full
+# captures (a number taken under a profiler cannot be re-measured inside a timed run): separate compositing / fused
+NCU_FINE_LAUNCH_DRAM_BYTES = {False: 542_652_160 + 1_917_181_000, True: 528_085_248 + 20_951_296}
+NCU_TRAFFIC_SOURCE = {False: "static, from profiles/r1_bench_fine_launch_ncu_key_metrics.txt (dram read + write of this launch, ncu --set full); not measured in this run",
+                      True: "static, from profiles/r2_bench_fine_launch_ncu_key_metrics.txt (dram read + write of this launch, ncu --set full); not measured in this run"}
 CPU_SAMPLE_RAYS = 4096
 WORKLOAD = ("single-B200 full-frame 800x800 render per GPU (BASELINE configs[1]); view r of N per rank, "
             "random-init 8x256 NeRF MLPs (seeds 0/1), L=10/4 PE")
@@ -518,8 +521,8 @@ def main():
         roofline = {"bound": "tensor", "kernel": "k_mlp_tc (fine pass, 192 samples/ray)" if use_bf16 else "k_mlp_fp32",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "peak_kind": f"sustained, {peaks['source']}",
-                    "traffic": NCU_FINE_LAUNCH_DRAM_BYTES if (use_bf16 and R == 640000 and not fused) else None,
-                    "traffic_source": NCU_TRAFFIC_SOURCE,
+                    "traffic": NCU_FINE_LAUNCH_DRAM_BYTES[fused] if (use_bf16 and R == 640000) else None,
+                    "traffic_source": NCU_TRAFFIC_SOURCE[fused],
                     # z read (4 B/sample) + raw written (16 B/sample) -- or, with compositing fused in, the four maps
                     "algorithmic_hbm_bytes": R * (N_C + N_F) * 4 + (R * 28 if fused else R * (N_C + N_F) * 16),
                     "composite_fused": fused,
