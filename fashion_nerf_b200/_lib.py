@@ -87,6 +87,7 @@ SIGNATURES = {
     "fnerf_render_rays_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "fnerf_render_rays": (c_int, [ctypes.POINTER(RenderArgs), c_void_p]),
     "fnerf_debug_pipe_stats": (c_int, [c_void_p]),
+    "fnerf_debug_fdiv_mismatches": (c_int, [c_int64, ctypes.c_uint64, c_void_p, c_void_p]),
     "fnerf_debug_wgrad_tc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64, c_int, c_int64, c_void_p]),
 }
 

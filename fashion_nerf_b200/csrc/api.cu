@@ -85,6 +85,12 @@ int fnerf_stratified(const float* near, const float* far, const float* t_vals, c
   return launch_stratified(near, far, t_vals, u_strat, z, R, N, lindisp, (cudaStream_t)stream);
 }
 
+int fnerf_debug_fdiv_mismatches(int64_t n, uint64_t seed, unsigned long long* mismatches, fnerf_stream_t stream) {
+  FN_REQUIRE(n >= 0, FNERF_ERR_SIZE, "debug_fdiv: n < 0");
+  FN_REQUIRE(mismatches, FNERF_ERR_NULL, "debug_fdiv: null pointer");
+  return launch_debug_fdiv(n, seed, mismatches, (cudaStream_t)stream);
+}
+
 int fnerf_importance(const float* z_c, const float* weights_c, const float* u, int64_t u_row_stride,
                      float* z_samples, float* z_f, int32_t* bin_idx, float* z_std, int64_t R,
                      int64_t Nc, int64_t Nf, fnerf_stream_t stream) {

@@ -73,6 +73,7 @@ int launch_stratified(const float* near, const float* far, const float* t_vals, 
 int launch_importance(const float* z_c, const float* w_c, const float* u, int64_t u_stride,
                       float* z_samples, float* z_f, int32_t* bin_idx, float* z_std, int64_t R,
                       int64_t Nc, int64_t Nf, cudaStream_t s);
+int launch_debug_fdiv(int64_t n, uint64_t seed, unsigned long long* mismatches, cudaStream_t s);
 int launch_posenc(const float* x, float* out, int64_t M, int L, cudaStream_t s);
 int launch_composite_fwd(const float* raw, const float* z, const float* dnorm, const float* noise,
                          float* rgb, float* depth, float* acc, float* disp, float* weights,

@@ -341,13 +341,13 @@ def test_composite_bwd_with_raw_noise(F, cuda_device, R, S, white):
     assert (fwd["rgb"].cpu() - ref["rgb"]).abs().max() <= 1e-5 and (fwd["weights"].cpu() - ref["weights"]).abs().max() <= 1e-5
 
 
-@pytest.mark.parametrize("Nc,Nf", [(64, 128), (32, 32), (64, 64), (128, 128), (128, 256)])
+@pytest.mark.parametrize("Nc,Nf", [(64, 128), (32, 32), (64, 64), (128, 128), (128, 256), (256, 768)])
 @pytest.mark.parametrize("kind", ["random", "linspace_row", "sorted", "peaky", "descending"])
 def test_importance_register_path_bit_exact(F, cuda_device, Nc, Nf, kind):
-    """The register-resident kernels (Nc = 32*2^a, Nf = 32*2^b): bit-exact indices, samples and merged depths for random
-    uniforms, the shared deterministic row (sort skipped), per-ray sorted uniforms, peaky weights (many samples in one
-    bin, duplicates) and descending coarse depths (slow in-kernel path)."""
-    R = 777
+    """The register-resident kernels (Nc = 32*2^a, Nf = 32*b; 256 + 768 pads its 24 samples per lane to 32): bit-exact
+    indices, samples and merged depths for random uniforms, the shared deterministic row (sort skipped), per-ray sorted
+    uniforms, peaky weights (many samples in one bin, duplicates) and descending coarse depths (slow in-kernel path)."""
+    R = 777 if Nf < 768 else 301
     g = _gen(Nc * 1000 + Nf)
     if kind == "descending":
         z = O.stratified(torch.full((R,), 6.0), torch.full((R,), 2.0), torch.linspace(0, 1, Nc), torch.rand(R, Nc, generator=g))
@@ -370,3 +370,33 @@ def test_importance_register_path_bit_exact(F, cuda_device, Nc, Nf, kind):
     assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
     assert torch.equal(got["z_f"].cpu(), ref["z_f"])
     assert torch.allclose(got["z_std"].cpu(), ref["z_std"], rtol=1e-4, atol=1e-6)
+
+
+def test_importance_fast_division_matches_ieee(F, cuda_device):
+    """The inverse CDF divides with div.rn.f32's fast-path instruction sequence behind its own range test
+    (sampling.cu fdiv_rn_inrange): bit-identical to IEEE division on 2^28 pairs of the ranges the kernel produces."""
+    lib = F.load_library()
+    bad = torch.zeros(2, dtype=torch.int64, device=cuda_device)
+    for seed in (1, 2):
+        assert lib.fnerf_debug_fdiv_mismatches(1 << 27, seed, bad.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    n_bad, pair = int(bad[0].item()), int(bad[1].item()) & (2 ** 64 - 1)
+    assert n_bad == 0, f"{n_bad} mismatches, e.g. x bits {pair >> 32:#010x}, d bits {pair & 0xffffffff:#010x}"
+
+
+def test_importance_tiny_and_huge_uniforms_take_the_ieee_division(F, cuda_device):
+    """Numerators outside the fast division's range (denormal / tiny u in the first bin, u far above 1, negative u) go
+    through __fdiv_rn: still bit-exact on the register path."""
+    R, Nc, Nf = 64, 64, 128
+    z, w = _coarse_case(R, Nc, 77)
+    u = torch.rand(R, Nf, generator=_gen(78))
+    u[:, 3] = 1e-42
+    u[:, 40] = 3e-33
+    u[:, 77] = 0.0
+    u[1::2, 100] = 2.5e31
+    u[0::2, 101] = -1e-35
+    ref = O.sample_pdf(z, w, u)
+    got = F.ops.importance(z.to(cuda_device), w.to(cuda_device), u.to(cuda_device))
+    assert torch.equal(got["inds"].cpu().long(), ref["inds"])
+    assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
+    assert torch.equal(got["z_f"].cpu(), ref["z_f"])
