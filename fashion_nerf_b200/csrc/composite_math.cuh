@@ -11,9 +11,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// sigmoid through ex2.approx + rcp-based division (~6 instructions instead of ~30): relative error ~3e-7, which
-// enters the maps linearly (weights sum to <= 1); the transmittance product keeps the exact expf
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid through ex2.approx + rcp.approx (4 instructions: FMUL, MUFU.EX2, FADD, MUFU.RCP): relative error ~3e-7,
+// which enters the maps linearly (weights sum to <= 1); the transmittance product keeps the exact expf.  The .ftz forms
+// skip the denormal range fix-ups of __expf / __fdividef (8 instructions per sigmoid); results differ from those only
+// below 1e-38 (x > 87: 1 / (1 + 0) = 1 either way; x < -87: 0 either way).
+__device__ __forceinline__ float sigmoidf_(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 // alpha of one sample: sigma already includes the noise, dist = (z[i+1] - z[i]) * |d| (1e10 * |d| for the far sample)
 __device__ __forceinline__ float comp_alpha(float sigma, float dist, bool valid) {
@@ -40,21 +47,29 @@ struct CompSums { float r, g, b, d, w; };
 __device__ __forceinline__ void comp_accum(CompSums& a, float w, float sr, float sg, float sb, float zv) {
   a.r = fmaf(w, sr, a.r); a.g = fmaf(w, sg, a.g); a.b = fmaf(w, sb, a.b); a.d = fmaf(w, zv, a.d); a.w += w;
 }
-// warp reduction of the lanes' sums + the ray's maps (lane 0 stores)
+// warp reduction of the lanes' sums (every lane ends up with the totals)
+__device__ __forceinline__ void comp_reduce(CompSums& a) {
+  a.r = warp_sum(a.r); a.g = warp_sum(a.g); a.b = warp_sum(a.b); a.d = warp_sum(a.d); a.w = warp_sum(a.w);
+}
+// the maps of ray r from its totals (one thread)
+__device__ __forceinline__ void comp_store(const CompSums& a, int64_t r, int white, float* __restrict__ rgb_out,
+                                           float* __restrict__ depth_out, float* __restrict__ acc_out,
+                                           float* __restrict__ disp_out) {
+  const float bg = white ? (1.0f - a.w) : 0.0f;
+  rgb_out[3 * r] = a.r + bg;
+  rgb_out[3 * r + 1] = a.g + bg;
+  rgb_out[3 * r + 2] = a.b + bg;
+  depth_out[r] = a.d;
+  acc_out[r] = a.w;
+  const float q = a.d / a.w;              // NaN when acc == 0: propagated like torch.max does
+  disp_out[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
+}
+// warp reduction + the ray's maps (lane 0 stores)
 __device__ __forceinline__ void comp_finish(CompSums a, int lane, int64_t r, int white, float* __restrict__ rgb_out,
                                             float* __restrict__ depth_out, float* __restrict__ acc_out,
                                             float* __restrict__ disp_out) {
-  a.r = warp_sum(a.r); a.g = warp_sum(a.g); a.b = warp_sum(a.b); a.d = warp_sum(a.d); a.w = warp_sum(a.w);
-  if (lane == 0) {
-    const float bg = white ? (1.0f - a.w) : 0.0f;
-    rgb_out[3 * r] = a.r + bg;
-    rgb_out[3 * r + 1] = a.g + bg;
-    rgb_out[3 * r + 2] = a.b + bg;
-    depth_out[r] = a.d;
-    acc_out[r] = a.w;
-    const float q = a.d / a.w;              // NaN when acc == 0: propagated like torch.max does
-    disp_out[r] = 1.0f / ((q != q) ? q : fmaxf(1e-10f, q));
-  }
+  comp_reduce(a);
+  if (lane == 0) comp_store(a, r, white, rgb_out, depth_out, acc_out, disp_out);
 }
 
 }  // namespace fnerf
