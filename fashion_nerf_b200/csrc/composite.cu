@@ -85,25 +85,30 @@ k_composite_fwd(const float4* __restrict__ raw, const float* __restrict__ z,
 // A warp walks rays r0, r0 + W, r0 + 2W, ... (W = warps in the grid, so the device sweeps raw linearly) in passes of up to
 // 32: after the j-th ray's warp reduction lane j keeps the totals, and the per-ray scalar tail
 // (background, two IEEE divisions, six stores -- ~40 instructions that ran with one active lane per ray) is executed once
-// per pass with one lane per ray.  (Passes over 32 CONSECUTIVE rays were tried: coalesced map stores, but every warp then
-// streams its own 100 KB region and S = 192 fell from 0.88 to 0.81 of HBM.)  Same arithmetic per ray, same bits.
+// per pass with one lane per ray.  Short rays (S <= 64) instead take passes over up to 32 CONSECUTIVE rays (coalesced map
+// stores: 0.77 against 0.74 of HBM at S = 64); with longer rays every warp would stream its own 100 KB region and S = 192
+// falls from 0.91 to 0.81.  `batch` is 32 for the strided form; for the consecutive form it shrinks with R so that a
+// small launch (a 4096-ray training batch) still spreads over the device.  Same arithmetic per ray, same bits.
 template <int NB, bool kHasNoise>
 __global__ void __launch_bounds__(kCompWarps * 32)
 k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
                     const float* __restrict__ dnorm, const float* __restrict__ noise, float* __restrict__ rgb_out,
                     float* __restrict__ depth_out, float* __restrict__ acc_out,
-                    float* __restrict__ disp_out, float* __restrict__ weights, int64_t R, int S, int white) {
+                    float* __restrict__ disp_out, float* __restrict__ weights, int64_t R, int S, int white, int batch) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)gridDim.x * kCompWarps;
-  for (int64_t r0 = warp_global; r0 < R; r0 += warp_stride * 32) {
-    const int64_t left = (R - r0 + warp_stride - 1) / warp_stride;      // rays r0, r0 + stride, ... below R
-    const int nr = (int)(left < 32 ? left : 32);
-    const float dn_l = dnorm[r0 + (lane < nr ? lane : 0) * warp_stride];  // |d| of ray r0 + lane * stride
+  // short rays (NB <= 2): passes over `batch` CONSECUTIVE rays, long ones: rays W apart (see above)
+  constexpr bool kConsec = NB <= 2;
+  const int64_t rstep = kConsec ? 1 : warp_stride;
+  for (int64_t r0 = kConsec ? warp_global * batch : warp_global; r0 < R; r0 += warp_stride * batch) {
+    const int64_t left = (R - r0 + rstep - 1) / rstep;                  // rays r0, r0 + rstep, ... below R
+    const int nr = (int)(left < batch ? left : batch);
+    const float dn_l = dnorm[r0 + (lane < nr ? lane : 0) * rstep];      // |d| of this pass's lane-th ray
     CompSums keep = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int j = 0; j < nr; ++j) {
-      const int64_t r = r0 + j * warp_stride;
+      const int64_t r = r0 + j * rstep;
       const float4* rawr = raw + r * S;
       const float* zr = z + r * S;
       float4 rv[NB];
@@ -144,7 +149,7 @@ k_composite_fwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
       comp_reduce(a);
       if (lane == j) keep = a;
     }
-    if (lane < nr) comp_store(keep, r0 + lane * warp_stride, white, rgb_out, depth_out, acc_out, disp_out);
+    if (lane < nr) comp_store(keep, r0 + lane * rstep, white, rgb_out, depth_out, acc_out, disp_out);
   }
 }
 
@@ -157,9 +162,16 @@ int launch_composite_fwd(const float* raw, const float* z, const float* dnorm, c
   if (blocks > cap) blocks = cap;
   if (S <= 256) {
     const float4* raw4 = (const float4*)raw;
+    int64_t batch = 32;
+    if (S <= 64) {                                                    // consecutive passes (NB <= 2)
+      batch = R / ((int64_t)num_sms() * 64);                          // 32 once 64 warps per SM have a full pass
+      batch = batch < 1 ? 1 : (batch > 32 ? 32 : batch);
+      blocks = (R + batch * kCompWarps - 1) / (batch * kCompWarps);
+      if (blocks > cap) blocks = cap;
+    }
     const unsigned g = (unsigned)blocks, t = kCompWarps * 32;
-#define FN_FWD(NB) do { if (noise) k_composite_fwd_reg<NB, true><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); \
-                        else k_composite_fwd_reg<NB, false><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white); } while (0)
+#define FN_FWD(NB) do { if (noise) k_composite_fwd_reg<NB, true><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white, (int)batch); \
+                        else k_composite_fwd_reg<NB, false><<<g, t, 0, s>>>(raw4, z, dnorm, noise, rgb, depth, acc, disp, weights, R, (int)S, white, (int)batch); } while (0)
     switch ((S + 31) / 32) {
       case 1: FN_FWD(1); break;
       case 2: FN_FWD(2); break;
