@@ -400,3 +400,25 @@ def test_importance_tiny_and_huge_uniforms_take_the_ieee_division(F, cuda_device
     assert torch.equal(got["inds"].cpu().long(), ref["inds"])
     assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
     assert torch.equal(got["z_f"].cpu(), ref["z_f"])
+
+
+@pytest.mark.parametrize("R,S,white", [(28421, 64, False), (47371, 32, True), (80003, 192, True), (76543, 100, False)])
+def test_composite_fwd_multi_ray_passes(F, cuda_device, R, S, white):
+    """Launch sizes at which a warp of the register-resident forward walks SEVERAL rays per pass (lane j keeps the j-th
+    ray's totals, one lane per ray runs the scalar tail): consecutive rays for S <= 64 (pass length R / (64 warps x SMs),
+    ragged last pass), rays one grid apart above.  Per-ray maps against the oracle, ray by ray."""
+    g = _gen(R + S)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0]
+    raw = torch.randn(R, S, 4, generator=g)
+    dn = 1 + torch.rand(R, generator=g)
+    ref = O.raw2outputs(raw, z, dn, white)
+    got = F.ops.composite_fwd(raw.to(cuda_device), z.to(cuda_device), dn.to(cuda_device), white_bkgd=white)
+    for k in ("rgb", "acc", "weights"):
+        assert (got[k].cpu() - ref[k]).abs().max() <= 1e-5, k
+    assert (got["depth"].cpu() - ref["depth"]).abs().max() <= 1e-5 * 6
+    assert torch.allclose(got["disp"].cpu(), ref["disp"], rtol=1e-4, atol=1e-6, equal_nan=True)
+    # the same rays in a small launch (one ray per pass) give the same bits
+    sl = slice(R - 1000, R)
+    small = F.ops.composite_fwd(raw[sl].to(cuda_device), z[sl].to(cuda_device), dn[sl].to(cuda_device), white_bkgd=white)
+    for k in ("rgb", "acc", "depth", "disp", "weights"):
+        assert torch.equal(small[k], got[k][sl]) or (k == "disp" and torch.equal(small[k].isnan(), got[k][sl].isnan())), k
