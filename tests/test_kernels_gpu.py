@@ -422,3 +422,18 @@ def test_composite_fwd_multi_ray_passes(F, cuda_device, R, S, white):
     small = F.ops.composite_fwd(raw[sl].to(cuda_device), z[sl].to(cuda_device), dn[sl].to(cuda_device), white_bkgd=white)
     for k in ("rgb", "acc", "depth", "disp", "weights"):
         assert torch.equal(small[k], got[k][sl]) or (k == "disp" and torch.equal(small[k].isnan(), got[k][sl].isnan())), k
+
+
+@pytest.mark.parametrize("Nc,Nf,R", [(64, 128, 30011), (32, 32, 25007), (128, 256, 12001)])
+def test_importance_register_path_many_rays_per_warp(F, cuda_device, Nc, Nf, R):
+    """More rays than warps in the grid: every warp reuses its shared-memory tables (cdf, gather entries, sorted samples /
+    the prefix-maximum table, merged row) for several rays in a row.  Bit-exact against the oracle, mixed sorted and
+    unsorted uniform rows so that consecutive rays of a warp take the sort and the skip-sort branch."""
+    z, w = _coarse_case(R, Nc, R % 97, peaky=True)
+    u = torch.rand(R, Nf, generator=_gen(R))
+    u[::3] = torch.sort(u[::3], -1)[0]
+    ref = O.sample_pdf(z, w, u)
+    got = F.ops.importance(z.to(cuda_device), w.to(cuda_device), u.to(cuda_device))
+    assert torch.equal(got["inds"].cpu().long(), ref["inds"])
+    assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
+    assert torch.equal(got["z_f"].cpu(), ref["z_f"])
