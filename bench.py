@@ -405,6 +405,41 @@ def bench_strong(F, cx: Ctx, model):
     return rec
 
 
+def bench_cond(F, cx: Ctx):
+    """BASELINE configs[4]: the garment-latent-conditioned network (256-d code joined at the skip layer), 32 views of
+    512x512, one code per view, views dealt round-robin to the ranks.  Every rank times TWO of its views per pass (524,288
+    rays; the full configuration is 16 such passes at N = 1), max over ranks, no collective."""
+    dev, world, rank = cx.dev, cx.world, cx.rank
+    HH = WW = 512
+    V, per_pass = 32, 2
+    mine = [v for v in range(V) if v % world == rank][:per_pass]
+    os_, ds_, vid = [], [], []
+    for v in mine:
+        a, b = F.pinhole_rays(HH, WW, view=v, n_views=V)
+        os_.append(a); ds_.append(b); vid.append(torch.full((HH * WW,), v, dtype=torch.int32))
+    o, d, view_id = torch.cat(os_).to(dev), torch.cat(ds_).to(dev), torch.cat(vid).to(dev)
+    codes = torch.randn(V, 256, generator=torch.Generator().manual_seed(2)).to(dev)
+    cmodel = F.NerfModel.random(dev, cond=True)
+    n = o.shape[0]
+    g = torch.Generator(device=dev).manual_seed(11)
+    u_s, u_f = torch.rand(n, N_C, device=dev, generator=g), torch.rand(n, N_F, device=dev, generator=g)
+
+    def render():
+        with torch.no_grad():
+            return F.render_rays(cmodel, o, d, NEAR, FAR, N_C, N_F, codes, view_id=view_id, u_strat=u_s, u_fine=u_f)["rgb"]
+
+    ms = cx.timed(render, reps=3, warm=1)
+    rec = {"workload": "BASELINE configs[4]: garment-latent-conditioned NeRF, 32 views of 512x512, one 256-d code per view, "
+                       "64+128 samples; two views per rank per pass, views round-robin over the ranks",
+           "views_per_pass_per_gpu": len(mine), "rays_per_gpu_per_pass": n, "n_gpus": world, "ms_per_pass": round(ms, 3),
+           "Mrays_s": round(world * n / (ms * 1e-3) / 1e6, 4),
+           "tflops_per_gpu": round(n * FLOP_PER_RAY / (ms * 1e-3) / 1e12, 1),
+           "full_config_s": round(V * HH * WW / (world * n) * ms * 1e-3, 3)}
+    del cmodel, o, d, u_s, u_f
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -497,6 +532,7 @@ def main():
     if not args.only_render and args.precision == "bf16":
         extra["train"] = bench_train(F, cx, peaks, steps=max(steps, 20))
         extra["strong"] = bench_strong(F, cx, model)
+        extra["cond"] = bench_cond(F, cx)
         if world == 1:
             extra["roofline_stages"] = bench_stages(F, cx, peaks)
             # the fp32 SIMT path of configs[1] ("bf16 tcgen05 path vs fp32 CUDA path") on 1/8 of the frame (~1 s per pass)
