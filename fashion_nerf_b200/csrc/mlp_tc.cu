@@ -423,8 +423,31 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
       __syncwarp();
       return;
 #endif
+#ifdef EXP_TAPE_NOLD
+      if (P.M >= 0) { __syncwarp(); return; }     // experiment: the hand-shake alone, no shared-memory read-out, no stores
+#endif
       const uint32_t src = src_img + ((uint32_t)lane << 4);
       uint8_t* dstg = dst_img + ((uint32_t)lane << 4);
+#if defined(EXP_TAPE_LDONLY)
+      // experiment: read the image out of shared memory, store nothing (one guard at the end keeps the loads alive)
+      uint32_t acc_x = 0u;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        uint4 t4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t4[j] = ld_shared_v4(src + (uint32_t)(b * 8 + j) * 512u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc_x ^= t4[j].x ^ t4[j].y ^ t4[j].z ^ t4[j].w;
+      }
+      if (acc_x == 0x12345678u && P.M < 0) *reinterpret_cast<uint32_t*>(dstg) = acc_x;
+#elif defined(EXP_TAPE_STONLY)
+      // experiment: store the image bytes' worth of a register pattern, read nothing from shared memory
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dstg + (b * 8 + j) * 512), "r"(src), "r"(src), "r"(src), "r"(src) : "memory");
+#else
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         uint4 t4[8];
@@ -437,6 +460,7 @@ __global__ void __launch_bounds__(kSave ? kTcThreads + 32 * kTapeWarps : kTcThre
 #endif
           asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dstg + (b * 8 + j) * 512), "r"(t4[j].x), "r"(t4[j].y), "r"(t4[j].z), "r"(t4[j].w) : "memory");
       }
+#endif
       __syncwarp();                      // every lane's loads have returned (their stores consumed them)
     };
     // A waiter must observe a barrier phase before the NEXT phase of that barrier can complete (parity waits cannot tell
