@@ -4,7 +4,7 @@ import fashion_nerf_b200 as F
 dev = torch.device("cuda:0")
 model = F.NerfModel.random(dev)
 o_all, d_all = F.pinhole_rays(800, 800)
-n = 80000
+n = int(os.environ.get("FP32_RAYS", "80000"))
 o, d = o_all[:n].to(dev), d_all[:n].to(dev)
 g = torch.Generator(device=dev).manual_seed(0)
 us, uf = torch.rand(n, 64, device=dev, generator=g), torch.rand(n, 128, device=dev, generator=g)
