@@ -381,6 +381,121 @@ k_composite_bwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
   }
 }
 
+// Backward for 256 < S <= 1024: ceil(S / 128) warps share a ray, each holds one 128-sample chunk in registers exactly like
+// k_composite_bwd_reg<4> (raw and z read ONCE, nothing recomputed), and the chunks exchange two scalars through shared
+// memory: the product of (1 - alpha + 1e-10) over a chunk (transmittance entering the later chunks; T enters every term
+// linearly, so a chunk scans with carry 1 and scales afterwards) and the chunk's sum of w*v (the suffix sum entering the
+// earlier chunks).  The shared-memory kernel above re-reads raw and z in its second pass (ncu at S = 1024: 43 % more DRAM
+// reads than algorithmic, 8.5 k warp instructions per ray, 0.37 of HBM) and stays for S > 1024.
+constexpr int kLongNB = 4;                                   // 32-sample blocks per warp (8 or 2: slower, 3.1 / 3.6 vs 4.1 TB/s at S = 1024)
+constexpr int kLongMaxWarps = 8;                             // warps per ray = ceil(S / 128) <= 8
+template <int kLongWarps, bool kHasNoise>
+__global__ void __launch_bounds__(kLongWarps * 32)
+k_composite_bwd_long(const float4* __restrict__ raw, const float* __restrict__ z,
+                     const float* __restrict__ dnorm, const float* __restrict__ noise, const float* __restrict__ g_rgb,
+                     const float* __restrict__ g_depth, const float* __restrict__ g_acc,
+                     float4* __restrict__ g_raw, int64_t R, int S, int white) {
+  constexpr int NB = kLongNB;
+  __shared__ float s_prod[2][kLongWarps], s_sum[2][kLongWarps];       // double-buffered by ray parity: one barrier per ray
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base = warp * (NB * 32);
+  int par = 0;
+  for (int64_t r = blockIdx.x; r < R; r += gridDim.x, par ^= 1) {
+    const float4* rawr = raw + r * S;
+    const float* zr = z + r * S;
+    float4 rv[NB];
+    float zv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = base + b * 32 + lane;
+      rv[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      zv[b] = 0.f;
+      if (i < S) {
+        rv[b] = ldg_stream4(rawr + i); zv[b] = ldg_stream(zr + i);
+        if (kHasNoise) rv[b].w += ldg_stream(noise + r * S + i);
+      }
+    }
+    const float z_chunk_next = (base + NB * 32 < S) ? zr[base + NB * 32] : 0.f;   // first depth of the next chunk
+    const float dn = dnorm[r];
+    const float gr = g_rgb[3 * r], gg = g_rgb[3 * r + 1], gb = g_rgb[3 * r + 2];
+    const float gd = g_depth ? g_depth[r] : 0.0f;
+    float ga = g_acc ? g_acc[r] : 0.0f;
+    if (white) ga -= (gr + gg + gb);
+
+    float Tb[NB], alb[NB], distb[NB], vb[NB];
+    float carry = 1.0f;                            // relative to the chunk's first sample
+    float wsum = 0.0f;                             // this lane's share of sum alpha * T_rel * v
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i = base + b * 32 + lane;
+      Tb[b] = 0.f; alb[b] = 0.f; distb[b] = 0.f; vb[b] = 0.f;
+      if (base + b * 32 < S) {                     // warp-uniform
+        float z_up = __shfl_down_sync(0xffffffffu, zv[b], 1);
+        const float z_first_next = (b + 1 < NB) ? __shfl_sync(0xffffffffu, zv[(b + 1 < NB) ? b + 1 : b], 0) : z_chunk_next;
+        if (lane == 31) z_up = z_first_next;
+        const bool valid = i < S;
+        float dist = (i == S - 1) ? 1e10f : (z_up - zv[b]);
+        dist *= dn;
+        const float alpha = valid ? (1.0f - expf(-fmaxf(rv[b].w, 0.0f) * dist)) : 0.0f;
+        float p = valid ? (1.0f - alpha + 1e-10f) : 1.0f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_up_sync(0xffffffffu, p, o);
+          if (lane >= o) p *= n;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, p, 1);
+        if (lane == 0) excl = 1.0f;
+        Tb[b] = carry * excl;
+        carry *= __shfl_sync(0xffffffffu, p, 31);
+        alb[b] = alpha;
+        distb[b] = dist;
+        vb[b] = valid ? (gr * sigmoidf_(rv[b].x) + gg * sigmoidf_(rv[b].y) + gb * sigmoidf_(rv[b].z) + gd * zv[b] + ga) : 0.0f;
+        wsum += alpha * Tb[b] * vb[b];
+      }
+    }
+    wsum = warp_sum(wsum);
+    if (lane == 0) { s_prod[par][warp] = carry; s_sum[par][warp] = wsum; }
+    asm volatile("bar.sync 2, %0;" ::"n"(kLongWarps * 32) : "memory");
+    float cin = 1.0f;                              // transmittance entering this chunk
+    float tail = 0.0f;                             // sum of w*v over the later chunks
+    {
+      float run = 1.0f;                            // transmittance entering chunk w2
+#pragma unroll
+      for (int w2 = 0; w2 < kLongWarps; ++w2) {
+        if (w2 == warp) cin = run;
+        if (w2 > warp) tail += run * s_sum[par][w2];
+        run *= s_prod[par][w2];
+      }
+    }
+#pragma unroll
+    for (int b = NB - 1; b >= 0; --b) {
+      const int i = base + b * 32 + lane;
+      if (base + b * 32 < S) {
+        const bool valid = i < S;
+        const float T = cin * Tb[b];
+        const float wv = valid ? alb[b] * T * vb[b] : 0.0f;
+        float q = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_down_sync(0xffffffffu, q, o);
+          if (lane + o < 32) q += n;
+        }
+        const float suffix = (q - wv) + tail;
+        tail += __shfl_sync(0xffffffffu, q, 0);
+        if (valid) {
+          const float om = 1.0f - alb[b] + 1e-10f;
+          const float w = alb[b] * T;
+          const float cr = sigmoidf_(rv[b].x), cg = sigmoidf_(rv[b].y), cb = sigmoidf_(rv[b].z);
+          const float g_alpha = T * vb[b] - suffix / om;
+          const float g_sigma = (rv[b].w > 0.0f) ? distb[b] * (1.0f - alb[b]) * g_alpha : 0.0f;
+          g_raw[r * S + i] = make_float4(w * gr * cr * (1.0f - cr), w * gg * cg * (1.0f - cg),
+                                         w * gb * cb * (1.0f - cb), g_sigma);
+        }
+      }
+    }
+  }
+}
+
 int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, const float* noise, const float* g_rgb,
                          const float* g_depth, const float* g_acc, float* g_raw, int64_t R,
                          int64_t S, int white, cudaStream_t s) {
@@ -401,6 +516,19 @@ int launch_composite_bwd(const float* raw, const float* z, const float* dnorm, c
       case 5: case 6: FN_BWD(6); break;
       default: FN_BWD(8); break;
     }
+    return check_launch("composite_bwd");
+  }
+  if (S <= kLongMaxWarps * kLongNB * 32) {
+    int64_t nb = R;
+    const int64_t capl = (int64_t)num_sms() * 32;
+    if (nb > capl) nb = capl;
+    const int W = (int)((S + kLongNB * 32 - 1) / (kLongNB * 32));     // 3..8
+#define FN_LONG(WW) case WW: \
+      if (noise) k_composite_bwd_long<WW, true><<<(unsigned)nb, WW * 32, 0, s>>>((const float4*)raw, z, dnorm, noise, g_rgb, g_depth, g_acc, (float4*)g_raw, R, (int)S, white); \
+      else k_composite_bwd_long<WW, false><<<(unsigned)nb, WW * 32, 0, s>>>((const float4*)raw, z, dnorm, noise, g_rgb, g_depth, g_acc, (float4*)g_raw, R, (int)S, white); \
+      break
+    switch (W) { FN_LONG(3); FN_LONG(4); FN_LONG(5); FN_LONG(6); FN_LONG(7); default: FN_LONG(8); }
+#undef FN_LONG
     return check_launch("composite_bwd");
   }
   const size_t smem = (size_t)kBwdWarps * 2 * S * sizeof(float);

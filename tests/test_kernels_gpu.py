@@ -437,3 +437,24 @@ def test_importance_register_path_many_rays_per_warp(F, cuda_device, Nc, Nf, R):
     assert torch.equal(got["inds"].cpu().long(), ref["inds"])
     assert torch.equal(got["z_samples"].cpu(), ref["z_samples"])
     assert torch.equal(got["z_f"].cpu(), ref["z_f"])
+
+
+@pytest.mark.parametrize("R,S,white", [(6001, 300, False), (5003, 777, True), (4801, 512, False), (4750, 1000, True)])
+def test_composite_bwd_long_rays_shared_by_warps(F, cuda_device, R, S, white):
+    """256 < S <= 1024: ceil(S / 128) warps share a ray and exchange the chunk transmittances / suffix sums through shared
+    memory; more rays than CTAs in the grid, so every CTA reuses the exchange buffers ray after ray (parity double
+    buffering).  Against the fp64 oracle, as close as the fp32 oracle is."""
+    g = _gen(R + S)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0]
+    raw = torch.randn(R, S, 4, generator=g)
+    dn = 1 + torch.rand(R, generator=g)
+    g_rgb, g_d, g_a = torch.randn(R, 3, generator=g), torch.randn(R, generator=g), torch.randn(R, generator=g)
+    ref64 = O.composite_bwd(raw.double(), z.double(), dn.double(), g_rgb.double(), g_d.double(), g_a.double(), white)
+    ref32 = O.composite_bwd(raw, z, dn, g_rgb, g_d, g_a, white)
+    dev = cuda_device
+    got = F.ops.composite_bwd(raw.to(dev), z.to(dev), dn.to(dev), g_rgb.to(dev), g_d.to(dev), g_a.to(dev), white_bkgd=white).cpu()
+    assert torch.isfinite(got).all()
+    err_kernel = (got.double() - ref64).abs().max().item()
+    err_oracle32 = (ref32.double() - ref64).abs().max().item()
+    scale = ref64.abs().max().item()
+    assert err_kernel <= max(4 * err_oracle32, 1e-5 * max(scale, 1.0)), (err_kernel, err_oracle32, scale)

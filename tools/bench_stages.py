@@ -24,7 +24,7 @@ def timeit(fn, iters=10, warm=3):
 
 out = {"R": R, "hbm_peak_gbs": HBM, "peak_source": "measured" if "when" in peaks else "fallback"}
 g = torch.Generator(device="cuda").manual_seed(0)
-for S in (64, 192):
+for S in (64, 192, 1024):
     z = torch.sort(torch.rand(R, S, device=dev, generator=g) * 4 + 2, -1)[0]
     raw = torch.randn(R, S, 4, device=dev, generator=g)
     dn = torch.ones(R, device=dev)
