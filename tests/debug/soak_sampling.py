@@ -1,8 +1,8 @@
 """Randomised soak of the register-path importance kernels and the compositing kernels against the oracle: many random
 launch sizes (odd R, more rays than warps in the grid), every dispatched shape, sorted / unsorted / shared uniform rows,
-peaky weights.  Bit-exact for importance, <= 1e-5 for compositing.  python tools/soak_sampling.py [iterations]"""
+peaky weights.  Bit-exact for importance, <= 1e-5 for compositing.  python tests/debug/soak_sampling.py [iterations]"""
 import os, sys, random, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import fashion_nerf_b200 as F
 from oracle import nerf_oracle as O
 dev = torch.device("cuda:0")
