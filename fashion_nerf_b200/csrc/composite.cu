@@ -371,7 +371,7 @@ k_composite_bwd_reg(const float4* __restrict__ raw, const float* __restrict__ z,
           const float w = alb[b] * Tb[b];
           const float cr = kKeepRgb ? crb[b] : sigmoidf_(rv[b].x), cg = kKeepRgb ? cgb[b] : sigmoidf_(rv[b].y),
                       cb = kKeepRgb ? cbb[b] : sigmoidf_(rv[b].z);
-          const float g_alpha = Tb[b] * vb[b] - suffix / om;
+          const float g_alpha = Tb[b] * vb[b] - __fdividef(suffix, om);
           const float g_sigma = (rv[b].w > 0.0f) ? distb[b] * (1.0f - alb[b]) * g_alpha : 0.0f;
           g_raw[r * S + i] = make_float4(w * gr * cr * (1.0f - cr), w * gg * cg * (1.0f - cg),
                                          w * gb * cb * (1.0f - cb), g_sigma);
@@ -486,7 +486,7 @@ k_composite_bwd_long(const float4* __restrict__ raw, const float* __restrict__ z
           const float om = 1.0f - alb[b] + 1e-10f;
           const float w = alb[b] * T;
           const float cr = sigmoidf_(rv[b].x), cg = sigmoidf_(rv[b].y), cb = sigmoidf_(rv[b].z);
-          const float g_alpha = T * vb[b] - suffix / om;
+          const float g_alpha = T * vb[b] - __fdividef(suffix, om);
           const float g_sigma = (rv[b].w > 0.0f) ? distb[b] * (1.0f - alb[b]) * g_alpha : 0.0f;
           g_raw[r * S + i] = make_float4(w * gr * cr * (1.0f - cr), w * gg * cg * (1.0f - cg),
                                          w * gb * cb * (1.0f - cb), g_sigma);
