@@ -26,7 +26,7 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
 
 // ------------------------------------------------------------------------------------------ A.5
 template <bool kHasNoise>
-__global__ void __launch_bounds__(kCompWarps * 32)
+__global__ void __launch_bounds__(kCompWarps * 32, 8)     // latency-bound (one block in flight per warp): 32 registers, 8 CTAs per SM
 k_composite_fwd(const float4* __restrict__ raw, const float* __restrict__ z,
                 const float* __restrict__ dnorm, const float* __restrict__ noise,
                 float* __restrict__ rgb_out, float* __restrict__ depth_out,

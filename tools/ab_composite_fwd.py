@@ -4,7 +4,7 @@ sys.path.insert(0, '.')
 import fashion_nerf_b200 as F
 from fashion_nerf_b200 import _lib
 dev = torch.device("cuda:0")
-S = int(sys.argv[1]); R = 1 << 19
+S = int(sys.argv[1]); R = 1 << (19 if S <= 256 else 17)
 g = torch.Generator(device=dev).manual_seed(0)
 raw = torch.randn(R, S, 4, device=dev, generator=g)
 z = torch.cumsum(torch.rand(R, S, device=dev, generator=g), -1) * (4.0 / S) + 2.0
